@@ -1,0 +1,99 @@
+"""tcgen05 GEMM (C-ABI tasr_gemm_bf16) against a float64 CPU contraction of the same bf16 inputs."""
+import pytest
+import torch
+
+from turkish_asr_model_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(A, B, a_mn, b_mn):
+    a = A.double().cpu()
+    b = B.double().cpu()
+    if a_mn:
+        a = a.t()
+    if b_mn:
+        b = b.t()
+    return a @ b.t()
+
+
+@pytest.mark.parametrize("debug", [False, True])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 256), (304, 200, 136), (2008, 1000, 256)])
+def test_gemm_store(cuda, M, N, K, a_mn, b_mn, debug):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K + a_mn * 2 + b_mn)
+    A = torch.randn((K, M) if a_mn else (M, K), generator=g).to(torch.bfloat16).to(cuda)
+    B = torch.randn((K, N) if b_mn else (N, K), generator=g).to(torch.bfloat16).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    out = torch.full((M, N), float("nan"), device=cuda, dtype=torch.float32)
+    L.gemm(M, N, K, A, A.stride(0), B, B.stride(0), L.EPI_STORE, out, N, a_mn=a_mn, b_mn=b_mn, out_f32=1,
+           bias=bias, debug=debug)
+    torch.cuda.synchronize()
+    ref = _ref(A, B, a_mn, b_mn) + bias.double().cpu()
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert err < 2e-3 * (K ** 0.5), f"max err {err}"
+
+
+def test_gemm_swiglu_and_bwd(cuda):
+    M, d, dff = 384, 256, 1024
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(M, d, generator=g)).to(torch.bfloat16).to(cuda)
+    W = (torch.randn(2 * dff, d, generator=g) / 16).to(torch.bfloat16).to(cuda)
+    b = torch.randn(2 * dff, generator=g).to(cuda)
+    gv = torch.empty(M, 2 * dff, device=cuda, dtype=torch.bfloat16)
+    h = torch.empty(M, dff, device=cuda, dtype=torch.bfloat16)
+    L.gemm(M, dff, d, x, d, W, d, L.EPI_SWIGLU, h, dff, out2=gv, ldo2=2 * dff, bias=b, n_half=dff)
+    torch.cuda.synchronize()
+    ref = x.double().cpu() @ W.double().cpu().t() + b.double().cpu()
+    assert (gv.double().cpu() - ref).abs().max().item() < 0.05
+    gq, vq = gv.double().cpu()[:, :dff], gv.double().cpu()[:, dff:]
+    href = torch.nn.functional.silu(gq) * vq
+    assert (h.double().cpu() - href).abs().max().item() < 0.03 * href.abs().max().item()
+    # backward epilogue: dh = dy @ W2 with W2 (d, dff) used MN-major; out = dg|dv
+    dy = torch.randn(M, d, generator=g).to(torch.bfloat16).to(cuda)
+    W2 = (torch.randn(d, dff, generator=g) / 16).to(torch.bfloat16).to(cuda)
+    dgv = torch.empty(M, 2 * dff, device=cuda, dtype=torch.bfloat16)
+    L.gemm(M, dff, d, dy, d, W2, dff, L.EPI_SWIGLU_BWD, dgv, 2 * dff, b_mn=1, aux=gv, ldaux=2 * dff, n_half=dff)
+    torch.cuda.synchronize()
+    dh = dy.double().cpu() @ W2.double().cpu()
+    s = torch.sigmoid(gq)
+    dg = dh * vq * (s * (1 + gq * (1 - s)))
+    dv = dh * gq * s
+    ref2 = torch.cat([dg, dv], 1)
+    assert (dgv.double().cpu() - ref2).abs().max().item() < 0.03 * ref2.abs().max().item()
+
+
+def test_gemm_wgrad_splitk_remap(cuda):
+    Mtok, N, K = 5000, 256, 512
+    g = torch.Generator().manual_seed(9)
+    dy = torch.randn(Mtok, N, generator=g).to(torch.bfloat16).to(cuda)
+    x = torch.randn(Mtok, K, generator=g).to(torch.bfloat16).to(cuda)
+    dW = torch.zeros(N, K, device=cuda)
+    L.gemm(N, K, Mtok, dy, N, x, K, L.EPI_ATOMIC, dW, K, a_mn=1, b_mn=1, split_k=8)
+    torch.cuda.synchronize()
+    ref = dy.double().cpu().t() @ x.double().cpu()
+    assert (dW.double().cpu() - ref).abs().max().item() < 0.02 * ref.abs().max().item()
+    # remapped columns: n -> (n % p0) * p1 + n / p0
+    dW2 = torch.zeros(N, K, device=cuda)
+    p0, p1 = 128, 4
+    L.gemm(N, K, Mtok, dy, N, x, K, L.EPI_ATOMIC, dW2, K, a_mn=1, b_mn=1, split_k=3, remap_p0=p0, remap_p1=p1)
+    torch.cuda.synchronize()
+    idx = torch.arange(K)
+    dst = (idx % p0) * p1 + idx // p0
+    ref2 = torch.zeros_like(ref)
+    ref2[:, dst] = ref
+    assert (dW2.double().cpu() - ref2).abs().max().item() < 0.02 * ref.abs().max().item()
+
+
+def test_gemm_resid(cuda):
+    M, N, K = 777, 256, 1024
+    g = torch.Generator().manual_seed(11)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).to(cuda)
+    B = (torch.randn(N, K, generator=g) / 32).to(torch.bfloat16).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    res = torch.randn(M, N, generator=g).to(cuda)
+    out = torch.empty_like(res)
+    L.gemm(M, N, K, A, K, B, K, L.EPI_RESID, out, N, bias=bias, aux=res, ldaux=N, alpha=0.5)
+    torch.cuda.synchronize()
+    ref = res.double().cpu() + 0.5 * (A.double().cpu() @ B.double().cpu().t() + bias.double().cpu())
+    assert (out.double().cpu() - ref).abs().max().item() < 1e-3
