@@ -121,6 +121,123 @@ int tasr_mel_forward(const float* wave, int64_t wave_ld, const int32_t* n_sample
                      int hop, int normalize, float* feats, void* workspace, size_t workspace_bytes,
                      tasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm over (channels-in-group x all padded time) per sample, token-major (B, T, d) fp32 input.
+ * Replaces: model/conformer.py:45-49 TransposeGroupNorm.forward (transpose + native_group_norm +
+ *   transpose), 5 uses per block (:121,124,78,133,135), and its backward.
+ *   stats (B, G, 2) fp32 = (mean, rstd) saved for backward.  out is bf16 (GEMM operand) or fp32.
+ *   bwd: dres (B,T,d) fp32 = (accumulate ? dres : 0) + dx;  dgamma/dbeta (d) are accumulated (+=).
+ * Requires d/G % 4 == 0 and d/4 a divisor of 256.
+ * ---------------------------------------------------------------------------------------------- */
+size_t tasr_groupnorm_workspace_bytes(int B, int T, int d);
+int tasr_groupnorm_fwd(const float* x, int B, int T, int d, int G, float eps, const float* gamma, const float* beta,
+                       void* out, int out_bf16, float* stats, void* workspace, size_t workspace_bytes,
+                       tasr_stream_t stream);
+int tasr_groupnorm_bwd(const void* dy, int dy_bf16, const float* x, int B, int T, int d, int G, const float* stats,
+                       const float* gamma, float* dres, int accumulate, float* dgamma, float* dbeta, void* workspace,
+                       size_t workspace_bytes, tasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Depthwise Conv1d k=31 pad=15 along time (token-major bf16) with fused BatchNorm partial statistics;
+ * BatchNorm1d (batch statistics over B*T incl. padding, running-stat update) + SiLU.
+ * Replaces: model/conformer.py:83 depthwise_conv, :84 batch_norm, :85 swish (+ :82 GLU backward).
+ *   weight (d, 31) fp32 == the reference (d,1,31) tensor; bn_partial (tasr_dwconv_bn_parts, d, 2) fp32.
+ *   bn stats (d, 2) fp32 = (mean, rstd).
+ *   dwconv bwd: dw (M,d) bf16 in; ab (M,2d) saved GLU input (may be NULL -> du written to `du`);
+ *   dab (M,2d) bf16 out; dweight (d,31), dbias (d) accumulated (+=).
+ * ---------------------------------------------------------------------------------------------- */
+int tasr_dwconv_bn_parts(int B, int T);
+int tasr_dwconv31_fwd(const void* u, int B, int T, int d, const float* weight, const float* bias, void* out,
+                      float* bn_partial, tasr_stream_t stream);
+int tasr_dwconv31_bwd(const void* dw, const void* u, const void* ab, int B, int T, int d, const float* weight,
+                      void* dab, void* du, float* dweight, float* dbias, tasr_stream_t stream);
+int tasr_bn_finalize(const float* partial, int npart, int d, int64_t count, float eps, float momentum, int training,
+                     float* running_mean, float* running_var, int64_t* num_batches_tracked, float* stats,
+                     tasr_stream_t stream);
+int tasr_bn_silu_fwd(const void* w, int64_t M, int d, const float* stats, const float* gamma, const float* beta,
+                     void* out, tasr_stream_t stream);
+size_t tasr_bn_bwd_workspace_bytes(int64_t M, int d);
+int tasr_bn_silu_bwd(const void* ds, const void* w, int64_t M, int d, const float* stats, const float* gamma,
+                     const float* beta, void* dw, float* dgamma, float* dbeta, void* workspace,
+                     size_t workspace_bytes, tasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise helpers.
+ *   cast:   out_bf16[i] = bf16(alpha * in[i] * dropout_mask(seed, i))   (dropout backward of
+ *           model/conformer.py:25 + autocast casts)
+ *   colsum: out[c] += sum_r in[r][c]                                    (bias gradients)
+ *   rope:   in-place rotary embedding on the first rot_cols columns (64-wide heads) of (M, ld) bf16;
+ *           cos_sin (T, 32, 2) fp32; row r has position r % T.  model/attention.py:62-70,228-230.
+ * ---------------------------------------------------------------------------------------------- */
+int tasr_cast_f32_bf16(const float* in, void* out, int64_t n, float alpha, float drop_p, uint64_t seed,
+                       tasr_stream_t stream);
+int tasr_colsum_bf16(const void* in, int64_t M, int N, int64_t ld, float* out, tasr_stream_t stream);
+int tasr_rope_inplace(void* qkv, int64_t M, int T, int ld, int rot_cols, const float* cos_sin, int inverse,
+                      tasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-query flash attention (tcgen05), forward / backward.
+ * Replaces: model/attention.py:233-245 (expand + scaled_dot_product_attention / _standard_attention).
+ *   qkv (B*T, d+128) bf16 = q (H heads x 64) | k (64) | v (64), RoPE already applied to q and k.
+ *   key_lengths (B) int64 device or NULL: keys t >= key_lengths[b] are masked (reference mask
+ *   model/conformer.py:187-202).  A fully masked row yields 0.
+ *   ctx (B*T, d) bf16; lse2 (B, H, T) fp32 (log2 domain) saved for backward.
+ *   bwd: dqkv (B*T, d+128) bf16; with cos_sin != NULL the inverse RoPE is fused so that dqkv is the
+ *   gradient of the un-rotated projections.
+ * ---------------------------------------------------------------------------------------------- */
+int tasr_mqa_attention_fwd(const void* qkv, int B, int T, int H, int d, const int64_t* key_lengths, float drop_p,
+                           uint64_t seed, void* ctx, float* lse2, tasr_stream_t stream);
+size_t tasr_mqa_attention_bwd_workspace_bytes(int B, int T, int H, int d);
+int tasr_mqa_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse2, int B, int T, int H,
+                           int d, const int64_t* key_lengths, float drop_p, uint64_t seed, const float* cos_sin,
+                           void* dqkv, void* workspace, size_t workspace_bytes, tasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conv2d subsampler pieces (conv2 itself = tasr_gemm_bf16 on the im2col operand, SiLU epilogue).
+ * Replaces: model/conformer.py:150-155,177-183.
+ *   conv1_im2col: x (B,T,F) fp32 -> col (B*T2*F2, 9*d) bf16, column (kh*3+kw)*d + c,
+ *                 value silu(conv1(x))[b,c,2*t2-1+kh,2*f2-1+kw] (0 in the padding).
+ *   col2im_conv1_bwd: dcol -> dW1 (d,1,3,3), db1 (d) accumulated (+=).
+ *   pack_weight_remap: out_bf16[n][(k % q)*(K/q) + k/q] = in_f32[n][k]  (conv2: q=9; input_proj: q=F2)
+ * ---------------------------------------------------------------------------------------------- */
+int tasr_conv1_im2col(const float* x, int B, int T, int F, int d, const float* w1, const float* b1, void* col,
+                      tasr_stream_t stream);
+int tasr_col2im_conv1_bwd(const void* dcol, const float* x, int B, int T, int F, int d, const float* w1,
+                          const float* b1, float* dw1, float* db1, tasr_stream_t stream);
+int tasr_pack_weight_remap(const float* in, int64_t N, int K, int q, void* out, tasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused log-softmax + CTC loss (mean reduction, zero_infinity) + gradient w.r.t. the logits.
+ * Replaces: trainer/trainer.py:167-173 (log_softmax + nn.CTCLoss(blank=0, zero_infinity=True)) and
+ *   their backward.  logits (B,T,V) bf16 or fp32; targets (B,Smax) int64 padded; lengths int64 (B),
+ *   all on the device.  loss (1) fp32 = mean_b(nll_b / max(S_b,1)), infeasible samples contribute 0;
+ *   nll (B) fp32 or NULL; dlogits same dtype/shape as logits (or NULL) =
+ *   grad_scale * (softmax - occupancy) / (B * max(S_b,1)) for t < input_lengths[b], else 0.
+ * ---------------------------------------------------------------------------------------------- */
+size_t tasr_ctc_workspace_bytes(int B, int T, int V, int Smax);
+int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int B, int T, int V, const int64_t* targets, int Smax,
+                          const int64_t* input_lengths, const int64_t* target_lengths, int blank, float grad_scale,
+                          float* loss, float* nll, void* dlogits, void* workspace, size_t workspace_bytes,
+                          tasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Global-norm clip + AdamW on flat fp32 buffers (also refreshes the bf16 shadow weights).
+ * Replaces: trainer/trainer.py:189-195, main.py:106-110.
+ *   hyper (9 floats, device): lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, max_norm, grad_div
+ *   sumsq (device double): sum of squared gradients (tasr_grad_sumsq, after all-reduce under DP).
+ * ---------------------------------------------------------------------------------------------- */
+int tasr_grad_sumsq(const float* g, int64_t n, double* out, tasr_stream_t stream);
+int tasr_clip_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, const float* hyper,
+                    const double* sumsq, float* norm_out, tasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Greedy CTC decode to token ids.  Replaces: utils/decoding.py:149,163; data/tokenizer.py:44-54.
+ *   ids (B,T) int64 argmax; tokens (B,T) int64 collapsed (repeats merged, blanks dropped, -1 padded);
+ *   out_len (B) int32.  lengths (B) int64 or NULL = frames to decode per utterance.
+ * ---------------------------------------------------------------------------------------------- */
+int tasr_argmax_collapse(const void* logits, int logits_bf16, int B, int T, int V, const int64_t* lengths, int blank,
+                         int64_t* ids, int64_t* tokens, int32_t* out_len, tasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,45 @@ LIB_PATH = os.path.join(_HERE, "libtasr_kernels.so")
 _lib = None
 
 
+
+P, I, L, F, Z, U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
+# every exported symbol of include/tasr_kernels.h (tests check the library exports all of them)
+_SIGNATURES = {
+    "tasr_version": (I, []),
+    "tasr_check_device": (I, []),
+    "tasr_init": (I, []),
+    "tasr_gemm_bf16": (I, [P, P]),
+    "tasr_gemm_bf16_debug": (I, [P, P]),
+    "tasr_mel_filter_ranges": (I, [P, I, P, P]),
+    "tasr_mel_workspace_bytes": (Z, [I, I]),
+    "tasr_mel_forward": (I, [P, L, P, I, I, P, P, P, I, I, I, I, P, P, Z, P]),
+    "tasr_groupnorm_workspace_bytes": (Z, [I, I, I]),
+    "tasr_groupnorm_fwd": (I, [P, I, I, I, I, F, P, P, P, I, P, P, Z, P]),
+    "tasr_groupnorm_bwd": (I, [P, I, P, I, I, I, I, P, P, P, I, P, P, P, Z, P]),
+    "tasr_dwconv_bn_parts": (I, [I, I]),
+    "tasr_dwconv31_fwd": (I, [P, I, I, I, P, P, P, P, P]),
+    "tasr_dwconv31_bwd": (I, [P, P, P, I, I, I, P, P, P, P, P, P]),
+    "tasr_bn_finalize": (I, [P, I, I, L, F, F, I, P, P, P, P, P]),
+    "tasr_bn_silu_fwd": (I, [P, L, I, P, P, P, P, P]),
+    "tasr_bn_bwd_workspace_bytes": (Z, [L, I]),
+    "tasr_bn_silu_bwd": (I, [P, P, L, I, P, P, P, P, P, P, P, Z, P]),
+    "tasr_cast_f32_bf16": (I, [P, P, L, F, F, U64, P]),
+    "tasr_colsum_bf16": (I, [P, L, I, L, P, P]),
+    "tasr_rope_inplace": (I, [P, L, I, I, I, P, I, P]),
+    "tasr_mqa_attention_fwd": (I, [P, I, I, I, I, P, F, U64, P, P, P]),
+    "tasr_mqa_attention_bwd_workspace_bytes": (Z, [I, I, I, I]),
+    "tasr_mqa_attention_bwd": (I, [P, P, P, P, I, I, I, I, P, F, U64, P, P, P, Z, P]),
+    "tasr_conv1_im2col": (I, [P, I, I, I, I, P, P, P, P]),
+    "tasr_col2im_conv1_bwd": (I, [P, P, I, I, I, I, P, P, P, P, P]),
+    "tasr_pack_weight_remap": (I, [P, L, I, I, P, P]),
+    "tasr_ctc_workspace_bytes": (Z, [I, I, I, I]),
+    "tasr_ctc_loss_fwd_bwd": (I, [P, I, I, I, I, P, I, P, P, I, F, P, P, P, P, Z, P]),
+    "tasr_grad_sumsq": (I, [P, L, P, P]),
+    "tasr_clip_adamw": (I, [P, P, P, P, P, L, P, P, P, P]),
+    "tasr_argmax_collapse": (I, [P, I, I, I, I, P, I, P, P, P, P]),
+}
+
+
 class TasrError(RuntimeError):
     pass
 
@@ -27,7 +66,10 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.tasr_status_string.restype = C.c_char_p
         _lib.tasr_last_error.restype = C.c_char_p
-        _lib.tasr_mel_workspace_bytes.restype = C.c_size_t
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
         if torch.cuda.is_available():
             rc = _lib.tasr_init()
             if rc != 0:
@@ -43,13 +85,24 @@ def check(rc):
 
 
 def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return torch.cuda.current_stream().cuda_stream
 
 
 def ptr(t):
-    if t is None:
-        return C.c_void_p(0)
-    return C.c_void_p(t.data_ptr())
+    return None if t is None else t.data_ptr()
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device):
+    """Reusable scratch buffer (per device); kernels of one stream run in order so sharing is safe."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
 
 
 def require_cuda(*ts):
@@ -100,7 +153,7 @@ def gemm(M, N, K, A, lda, B, ldb, epilogue, out, ldo, a_mn=0, b_mn=0, out_f32=0,
     a.alpha, a.n_half, a.drop_p, a.seed = alpha, n_half, drop_p, seed
     a.split_k, a.remap_p0, a.remap_p1 = split_k, remap_p0, remap_p1
     fn = lib().tasr_gemm_bf16_debug if debug else lib().tasr_gemm_bf16
-    check(fn(C.byref(a), stream_ptr()))
+    check(fn(C.addressof(a), stream_ptr()))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -122,7 +175,196 @@ def mel_forward(wave, n_samples, tmax, window, fb, ranges, normalize=True):
     feats = torch.empty(B, tmax, n_mels, dtype=torch.float32, device=wave.device)
     wsb = lib().tasr_mel_workspace_bytes(B, n_mels)
     ws = torch.empty(wsb, dtype=torch.uint8, device=wave.device)
-    check(lib().tasr_mel_forward(ptr(wave), C.c_int64(wave.stride(0)), ptr(n_samples), B, tmax, ptr(window), ptr(fb),
+    check(lib().tasr_mel_forward(ptr(wave), wave.stride(0), ptr(n_samples), B, tmax, ptr(window), ptr(fb),
                                  ptr(ranges), n_mels, 400, 160, int(bool(normalize)), ptr(feats), ptr(ws),
-                                 C.c_size_t(wsb), stream_ptr()))
+                                 wsb, stream_ptr()))
     return feats
+
+
+# ---------------------------------------------------------------------------------------------
+# GroupNorm
+# ---------------------------------------------------------------------------------------------
+def groupnorm_fwd(x, G, gamma, beta, eps=1e-5, out_bf16=True):
+    """x (B,T,d) fp32 -> (y, stats (B,G,2))."""
+    require_cuda(x, gamma, beta)
+    B, T, d = x.shape
+    y = torch.empty(B, T, d, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    stats = torch.empty(B, G, 2, dtype=torch.float32, device=x.device)
+    wsb = lib().tasr_groupnorm_workspace_bytes(B, T, d)
+    ws = workspace(wsb, x.device)
+    check(lib().tasr_groupnorm_fwd(ptr(x), B, T, d, G, eps, ptr(gamma), ptr(beta), ptr(y), int(out_bf16), ptr(stats),
+                                   ptr(ws), wsb, stream_ptr()))
+    return y, stats
+
+
+def groupnorm_bwd(dy, x, G, stats, gamma, dres, accumulate, dgamma, dbeta):
+    """dres (B,T,d) fp32 (+)= dx; dgamma/dbeta += ."""
+    require_cuda(dy, x, dres)
+    B, T, d = x.shape
+    wsb = lib().tasr_groupnorm_workspace_bytes(B, T, d)
+    ws = workspace(wsb, x.device)
+    check(lib().tasr_groupnorm_bwd(ptr(dy), int(dy.dtype == torch.bfloat16), ptr(x), B, T, d, G, ptr(stats), ptr(gamma),
+                                   ptr(dres), int(accumulate), ptr(dgamma), ptr(dbeta), ptr(ws), wsb, stream_ptr()))
+
+
+# ---------------------------------------------------------------------------------------------
+# depthwise conv + BatchNorm/SiLU
+# ---------------------------------------------------------------------------------------------
+def dwconv_fwd(u, weight, bias, want_stats=True):
+    """u (B,T,d) bf16; weight (d,31) fp32 -> (w (B,T,d) bf16, bn_partial)."""
+    require_cuda(u, weight, bias)
+    B, T, d = u.shape
+    out = torch.empty_like(u)
+    part = None
+    if want_stats:
+        part = torch.empty(lib().tasr_dwconv_bn_parts(B, T), d, 2, dtype=torch.float32, device=u.device)
+    check(lib().tasr_dwconv31_fwd(ptr(u), B, T, d, ptr(weight), ptr(bias), ptr(out), ptr(part), stream_ptr()))
+    return out, part
+
+
+def dwconv_bwd(dw, u, ab, weight, dweight, dbias):
+    require_cuda(dw, u, weight)
+    B, T, d = u.shape
+    dab = torch.empty(B, T, 2 * d, dtype=torch.bfloat16, device=u.device) if ab is not None else None
+    du = torch.empty_like(u) if ab is None else None
+    check(lib().tasr_dwconv31_bwd(ptr(dw), ptr(u), ptr(ab), B, T, d, ptr(weight), ptr(dab), ptr(du), ptr(dweight),
+                                  ptr(dbias), stream_ptr()))
+    return dab if ab is not None else du
+
+
+def bn_finalize(part, d, count, eps, momentum, training, running_mean, running_var, num_batches_tracked):
+    stats = torch.empty(d, 2, dtype=torch.float32, device=running_mean.device)
+    npart = part.shape[0] if part is not None else 0
+    check(lib().tasr_bn_finalize(ptr(part), npart, d, count, eps, momentum, int(training), ptr(running_mean),
+                                 ptr(running_var), ptr(num_batches_tracked), ptr(stats), stream_ptr()))
+    return stats
+
+
+def bn_silu_fwd(w, stats, gamma, beta):
+    M, d = w.numel() // w.shape[-1], w.shape[-1]
+    out = torch.empty_like(w)
+    check(lib().tasr_bn_silu_fwd(ptr(w), M, d, ptr(stats), ptr(gamma), ptr(beta), ptr(out), stream_ptr()))
+    return out
+
+
+def bn_silu_bwd(ds, w, stats, gamma, beta, dgamma, dbeta):
+    M, d = w.numel() // w.shape[-1], w.shape[-1]
+    dw = torch.empty_like(w)
+    wsb = lib().tasr_bn_bwd_workspace_bytes(M, d)
+    ws = workspace(wsb, w.device)
+    check(lib().tasr_bn_silu_bwd(ptr(ds), ptr(w), M, d, ptr(stats), ptr(gamma), ptr(beta), ptr(dw), ptr(dgamma),
+                                 ptr(dbeta), ptr(ws), wsb, stream_ptr()))
+    return dw
+
+
+# ---------------------------------------------------------------------------------------------
+# elementwise
+# ---------------------------------------------------------------------------------------------
+def cast_bf16(x, alpha=1.0, drop_p=0.0, seed=0, out=None):
+    require_cuda(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().tasr_cast_f32_bf16(ptr(x), ptr(out), x.numel(), alpha, drop_p, seed, stream_ptr()))
+    return out
+
+
+def colsum_add(x2d, out):
+    """out (N) fp32 += column sums of x2d (M,N) bf16."""
+    M, N = x2d.shape
+    check(lib().tasr_colsum_bf16(ptr(x2d), M, N, x2d.stride(0), ptr(out), stream_ptr()))
+
+
+def rope_inplace(qkv, T, rot_cols, cos_sin, inverse=False):
+    M, ld = qkv.shape
+    check(lib().tasr_rope_inplace(ptr(qkv), M, T, ld, rot_cols, ptr(cos_sin), int(inverse), stream_ptr()))
+
+
+# ---------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------
+def mqa_fwd(qkv, B, T, H, d, key_lengths, drop_p=0.0, seed=0):
+    require_cuda(qkv)
+    ctx = torch.empty(B * T, d, dtype=torch.bfloat16, device=qkv.device)
+    lse2 = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
+    check(lib().tasr_mqa_attention_fwd(ptr(qkv), B, T, H, d, ptr(key_lengths), drop_p, seed, ptr(ctx), ptr(lse2),
+                                       stream_ptr()))
+    return ctx, lse2
+
+
+def mqa_bwd(qkv, ctx, dctx, lse2, B, T, H, d, key_lengths, cos_sin, drop_p=0.0, seed=0):
+    dqkv = torch.empty_like(qkv)
+    wsb = lib().tasr_mqa_attention_bwd_workspace_bytes(B, T, H, d)
+    ws = workspace(wsb, qkv.device)
+    check(lib().tasr_mqa_attention_bwd(ptr(qkv), ptr(ctx), ptr(dctx), ptr(lse2), B, T, H, d, ptr(key_lengths), drop_p,
+                                       seed, ptr(cos_sin), ptr(dqkv), ptr(ws), wsb, stream_ptr()))
+    return dqkv
+
+
+# ---------------------------------------------------------------------------------------------
+# subsampler
+# ---------------------------------------------------------------------------------------------
+def sub_dims(T, F):
+    T1, F1 = (T - 1) // 2 + 1, (F - 1) // 2 + 1
+    return T1, F1, (T1 - 1) // 2 + 1, (F1 - 1) // 2 + 1
+
+
+def conv1_im2col(x, w1, b1):
+    require_cuda(x, w1, b1)
+    B, T, F = x.shape
+    d = w1.shape[0]
+    _, _, T2, F2 = sub_dims(T, F)
+    col = torch.empty(B * T2 * F2, 9 * d, dtype=torch.bfloat16, device=x.device)
+    check(lib().tasr_conv1_im2col(ptr(x), B, T, F, d, ptr(w1), ptr(b1), ptr(col), stream_ptr()))
+    return col
+
+
+def col2im_conv1_bwd(dcol, x, w1, b1, dw1, db1):
+    B, T, F = x.shape
+    d = w1.shape[0]
+    check(lib().tasr_col2im_conv1_bwd(ptr(dcol), ptr(x), B, T, F, d, ptr(w1), ptr(b1), ptr(dw1), ptr(db1), stream_ptr()))
+
+
+def pack_weight_remap(w2d, q):
+    N, K = w2d.shape
+    out = torch.empty(N, K, dtype=torch.bfloat16, device=w2d.device)
+    check(lib().tasr_pack_weight_remap(ptr(w2d), N, K, q, ptr(out), stream_ptr()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CTC, optimizer, decode
+# ---------------------------------------------------------------------------------------------
+def ctc_loss_fwd_bwd(logits, targets, input_lengths, target_lengths, blank=0, grad_scale=1.0, want_grad=True):
+    """logits (B,T,V) bf16|fp32; targets (B,Smax) int64; lengths int64 (device) -> (loss (1), nll (B), dlogits)."""
+    require_cuda(logits, targets, input_lengths, target_lengths)
+    B, T, V = logits.shape
+    Smax = targets.shape[1]
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    nll = torch.empty(B, dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty_like(logits) if want_grad else None
+    wsb = lib().tasr_ctc_workspace_bytes(B, T, V, Smax)
+    ws = workspace(wsb, logits.device)
+    check(lib().tasr_ctc_loss_fwd_bwd(ptr(logits), int(logits.dtype == torch.bfloat16), B, T, V, ptr(targets), Smax,
+                                      ptr(input_lengths), ptr(target_lengths), blank, grad_scale, ptr(loss), ptr(nll),
+                                      ptr(dlogits), ptr(ws), wsb, stream_ptr()))
+    return loss, nll, dlogits
+
+
+def grad_sumsq(g, out):
+    check(lib().tasr_grad_sumsq(ptr(g), g.numel(), ptr(out), stream_ptr()))
+
+
+def clip_adamw(p, g, m, v, shadow, hyper, sumsq, norm_out):
+    check(lib().tasr_clip_adamw(ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), p.numel(), ptr(hyper), ptr(sumsq),
+                                ptr(norm_out), stream_ptr()))
+
+
+def argmax_collapse(logits, lengths=None, blank=0):
+    require_cuda(logits)
+    B, T, V = logits.shape
+    ids = torch.empty(B, T, dtype=torch.int64, device=logits.device)
+    tokens = torch.empty(B, T, dtype=torch.int64, device=logits.device)
+    out_len = torch.empty(B, dtype=torch.int32, device=logits.device)
+    check(lib().tasr_argmax_collapse(ptr(logits), int(logits.dtype == torch.bfloat16), B, T, V, ptr(lengths), blank,
+                                     ptr(ids), ptr(tokens), ptr(out_len), stream_ptr()))
+    return ids, tokens, out_len

@@ -21,6 +21,7 @@ typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline long long imin64(long long a, long long b) { return a < b ? a : b; }
 
 // ----------------------------------------------------------------------------------------------
 // small device helpers

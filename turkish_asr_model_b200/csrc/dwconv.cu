@@ -1,0 +1,199 @@
+// Depthwise Conv1d (kernel 31, zero pad 15) along time on token-major (B, T, d) bf16 tensors, with the
+// BatchNorm partial statistics fused into the forward, and (backward) the weight / bias gradient and the
+// GLU backward fused into one kernel.  Halo tile staged in shared memory, sliding register window.
+// Replaces (reference): model/conformer.py:63-67,83 depthwise_conv (cuDNN depthwise + 2 transposes),
+//   the GLU backward of :82, and the statistics pass of BatchNorm1d :84.
+#include "common.cuh"
+
+namespace {
+
+constexpr int KW = 31, HALO = 15;
+constexpr int TT = 64;        // time steps per CTA
+constexpr int CC = 64;        // channels per CTA (32 bf16x2 lanes)
+constexpr int OPT = 8;        // outputs per thread
+constexpr int DW_THREADS = 256;  // 32 channel-pair lanes x 8 strips
+constexpr int ROWS = TT + 2 * HALO;
+
+__device__ __forceinline__ void load_tile(bf162 (*tile)[CC / 2], const bf16* __restrict__ src, int b, int T, int d, int t0,
+                                          int c0) {
+  // ROWS x 128 B, 8 threads (16 B each) per row
+  for (int i = threadIdx.x; i < ROWS * 8; i += DW_THREADS) {
+    const int r = i >> 3, v = i & 7;
+    const int t = t0 - HALO + r;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (t >= 0 && t < T) val = *reinterpret_cast<const uint4*>(src + ((long long)b * T + t) * d + c0 + v * 8);
+    *reinterpret_cast<uint4*>(&tile[r][v * 4]) = val;
+  }
+}
+
+// out[t] = bias + sum_k in[t + k - 15] * w[k]      (FLIP: w index 30 - k, used for the input gradient)
+template <bool FLIP>
+__device__ __forceinline__ void conv_strip(const bf162 (*tile)[CC / 2], int lane, int strip, const float2* wreg, float2* acc) {
+#pragma unroll
+  for (int j = 0; j < OPT + KW - 1; ++j) {
+    const float2 v = __bfloat1622float2(tile[strip * OPT + j][lane]);
+#pragma unroll
+    for (int o = 0; o < OPT; ++o) {
+      const int k = j - o;
+      if (k >= 0 && k < KW) {
+        const float2 w = wreg[FLIP ? (KW - 1 - k) : k];
+        acc[o].x = fmaf(v.x, w.x, acc[o].x);
+        acc[o].y = fmaf(v.y, w.y, acc[o].y);
+      }
+    }
+  }
+}
+
+// weight (d, 31) fp32 [reference layout (d,1,31)], bias (d)
+__global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const bf16* __restrict__ u, int T, int d,
+                                                                const float* __restrict__ weight,
+                                                                const float* __restrict__ bias, bf16* __restrict__ out,
+                                                                float* __restrict__ bn_partial) {
+  __shared__ __align__(16) bf162 tile[ROWS][CC / 2];
+  __shared__ float red[8][CC][2];
+  const int c0 = blockIdx.x * CC, t0 = blockIdx.y * TT, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, strip = threadIdx.x >> 5;
+  load_tile(tile, u, b, T, d, t0, c0);
+  float2 wreg[KW];
+  const int ch = c0 + 2 * lane;
+#pragma unroll
+  for (int k = 0; k < KW; ++k) wreg[k] = make_float2(weight[ch * KW + k], weight[(ch + 1) * KW + k]);
+  const float2 bv = make_float2(bias[ch], bias[ch + 1]);
+  __syncthreads();
+  float2 acc[OPT];
+#pragma unroll
+  for (int o = 0; o < OPT; ++o) acc[o] = bv;
+  conv_strip<false>(tile, lane, strip, wreg, acc);
+  float2 s = make_float2(0, 0), ss = make_float2(0, 0);
+#pragma unroll
+  for (int o = 0; o < OPT; ++o) {
+    const int t = t0 + strip * OPT + o;
+    if (t < T) {
+      bf162 q = __floats2bfloat162_rn(acc[o].x, acc[o].y);
+      *reinterpret_cast<bf162*>(out + ((long long)b * T + t) * d + ch) = q;
+      const float2 r = __bfloat1622float2(q);  // statistics of what BatchNorm will actually read
+      s.x += r.x; s.y += r.y;
+      ss.x += r.x * r.x; ss.y += r.y * r.y;
+    }
+  }
+  if (bn_partial != nullptr) {
+    red[strip][2 * lane][0] = s.x; red[strip][2 * lane][1] = ss.x;
+    red[strip][2 * lane + 1][0] = s.y; red[strip][2 * lane + 1][1] = ss.y;
+    __syncthreads();
+    if (threadIdx.x < CC * 2) {
+      const int c = threadIdx.x >> 1, which = threadIdx.x & 1;
+      float a = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a += red[r][c][which];
+      const long long part = (long long)b * gridDim.y + blockIdx.y;
+      bn_partial[(part * d + c0 + c) * 2 + which] = a;
+    }
+  }
+}
+
+// Backward: du = corr(dw, flipped weight); fused GLU backward -> dab (M, 2d);  dweight/dbias by atomics.
+__global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(const bf16* __restrict__ dwv, const bf16* __restrict__ u,
+                                                                const bf16* __restrict__ ab, int T, int d,
+                                                                const float* __restrict__ weight, bf16* __restrict__ dab,
+                                                                bf16* __restrict__ du_out, float* __restrict__ dweight,
+                                                                float* __restrict__ dbias) {
+  __shared__ __align__(16) bf162 tile[ROWS][CC / 2];   // dw with halo, later u with halo
+  __shared__ float red[CC][KW + 1];
+  const int c0 = blockIdx.x * CC, t0 = blockIdx.y * TT, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, strip = threadIdx.x >> 5;
+  const int ch = c0 + 2 * lane;
+  load_tile(tile, dwv, b, T, d, t0, c0);
+  for (int i = threadIdx.x; i < CC * (KW + 1); i += DW_THREADS) (&red[0][0])[i] = 0.f;
+  float2 wreg[KW];
+#pragma unroll
+  for (int k = 0; k < KW; ++k) wreg[k] = make_float2(weight[ch * KW + k], weight[(ch + 1) * KW + k]);
+  __syncthreads();
+  float2 acc[OPT];
+#pragma unroll
+  for (int o = 0; o < OPT; ++o) acc[o] = make_float2(0.f, 0.f);
+  conv_strip<true>(tile, lane, strip, wreg, acc);
+  // this thread's own dw values (centre rows) for the weight gradient
+  float2 g[OPT];
+  float2 gsum = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int o = 0; o < OPT; ++o) {
+    g[o] = __bfloat1622float2(tile[HALO + strip * OPT + o][lane]);
+    gsum.x += g[o].x; gsum.y += g[o].y;
+  }
+#pragma unroll
+  for (int o = 0; o < OPT; ++o) {
+    const int t = t0 + strip * OPT + o;
+    if (t < T) {
+      const long long row = (long long)b * T + t;
+      if (ab != nullptr) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + ch));
+        const float2 gt = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + d + ch));
+        const float s0 = sigmoidf_(gt.x), s1 = sigmoidf_(gt.y);
+        *reinterpret_cast<bf162*>(dab + row * 2 * d + ch) = __floats2bfloat162_rn(acc[o].x * s0, acc[o].y * s1);
+        *reinterpret_cast<bf162*>(dab + row * 2 * d + d + ch) =
+            __floats2bfloat162_rn(acc[o].x * a.x * s0 * (1.f - s0), acc[o].y * a.y * s1 * (1.f - s1));
+      }
+      if (du_out != nullptr)
+        *reinterpret_cast<bf162*>(du_out + row * d + ch) = __floats2bfloat162_rn(acc[o].x, acc[o].y);
+    }
+  }
+  __syncthreads();
+  load_tile(tile, u, b, T, d, t0, c0);
+  __syncthreads();
+  // dweight[c][k] = sum_t dw[t] * u[t + k - 15]
+  float2 wacc[KW];
+#pragma unroll
+  for (int k = 0; k < KW; ++k) wacc[k] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < OPT + KW - 1; ++j) {
+    const float2 v = __bfloat1622float2(tile[strip * OPT + j][lane]);
+#pragma unroll
+    for (int o = 0; o < OPT; ++o) {
+      const int k = j - o;
+      if (k >= 0 && k < KW) {
+        wacc[k].x = fmaf(g[o].x, v.x, wacc[k].x);
+        wacc[k].y = fmaf(g[o].y, v.y, wacc[k].y);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KW; ++k) {
+    atomicAdd(&red[2 * lane][k], wacc[k].x);
+    atomicAdd(&red[2 * lane + 1][k], wacc[k].y);
+  }
+  atomicAdd(&red[2 * lane][KW], gsum.x);
+  atomicAdd(&red[2 * lane + 1][KW], gsum.y);
+  __syncthreads();
+  for (int i = threadIdx.x; i < CC * (KW + 1); i += DW_THREADS) {
+    const int c = i / (KW + 1), k = i - c * (KW + 1);
+    const float v = red[c][k];
+    if (k < KW) atomicAdd(dweight + (long long)(c0 + c) * KW + k, v);
+    else if (dbias != nullptr) atomicAdd(dbias + c0 + c, v);
+  }
+}
+
+}  // namespace
+
+extern "C" int tasr_dwconv_bn_parts(int B, int T) { return B * cdiv(T, TT); }
+
+extern "C" int tasr_dwconv31_fwd(const void* u, int B, int T, int d, const float* weight, const float* bias,
+                                 void* out, float* bn_partial, tasr_stream_t stream) {
+  if (d % CC || B <= 0 || T <= 0) return TASR_ERR_SHAPE;
+  dim3 grid(d / CC, cdiv(T, TT), B);
+  dwconv_fwd_kernel<<<grid, DW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(u), T, d, weight, bias, reinterpret_cast<bf16*>(out), bn_partial);
+  TASR_CHECK_LAUNCH();
+  return TASR_OK;
+}
+
+extern "C" int tasr_dwconv31_bwd(const void* dw, const void* u, const void* ab, int B, int T, int d,
+                                 const float* weight, void* dab, void* du, float* dweight, float* dbias,
+                                 tasr_stream_t stream) {
+  if (d % CC || B <= 0 || T <= 0) return TASR_ERR_SHAPE;
+  dim3 grid(d / CC, cdiv(T, TT), B);
+  dwconv_bwd_kernel<<<grid, DW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(dw), reinterpret_cast<const bf16*>(u), reinterpret_cast<const bf16*>(ab), T, d,
+      weight, reinterpret_cast<bf16*>(dab), reinterpret_cast<bf16*>(du), dweight, dbias);
+  TASR_CHECK_LAUNCH();
+  return TASR_OK;
+}

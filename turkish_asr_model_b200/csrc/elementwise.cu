@@ -1,0 +1,129 @@
+// Small HBM-bound helpers: fp32 -> bf16 casts (with scale / dropout mask), column sums (bias
+// gradients), rotary position embedding on the fused QKV buffer.
+// Replaces (reference): autocast weight/activation casts; dropout backward of model/conformer.py:23,25;
+//   bias-gradient reductions of nn.Linear backward; model/attention.py:62-70,228-230 (rotate_half /
+//   apply_rotary_pos_emb: 2 x (chunk, neg, cat, mul, mul, add)).
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+__global__ void __launch_bounds__(NT) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
+                                                           long long n, float alpha, uint32_t thresh, float inv_keep,
+                                                           unsigned long long seed) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
+    float4 v = *reinterpret_cast<const float4*>(in + i * 4);
+    v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+    if (thresh) {
+      v.x *= dropout_scale(seed, i * 4 + 0, thresh, inv_keep);
+      v.y *= dropout_scale(seed, i * 4 + 1, thresh, inv_keep);
+      v.z *= dropout_scale(seed, i * 4 + 2, thresh, inv_keep);
+      v.w *= dropout_scale(seed, i * 4 + 3, thresh, inv_keep);
+    }
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i * 4) = u;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    float v = in[i] * alpha;
+    if (thresh) v *= dropout_scale(seed, i, thresh, inv_keep);
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// out[c] += sum_r in[r][c]   (in: (M, N) bf16, row pitch ld)
+__global__ void __launch_bounds__(NT) colsum_bf16_kernel(const bf16* __restrict__ in, long long M, int N, long long ld,
+                                                         int rows_per_cta, float* __restrict__ out) {
+  // blockDim = (32, 8): x -> column pair, y -> row lane
+  const int cp = blockIdx.x * 32 + threadIdx.x;  // column pair index
+  const long long r0 = (long long)blockIdx.y * rows_per_cta, r1 = min(M, r0 + (long long)rows_per_cta);
+  float2 acc = make_float2(0.f, 0.f);
+  const int c = cp * 2;
+  if (c + 1 < N) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      float2 v = __bfloat1622float2(*reinterpret_cast<const bf162*>(in + r * ld + c));
+      acc.x += v.x; acc.y += v.y;
+    }
+  } else if (c < N) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc.x += __bfloat162float(in[r * ld + c]);
+  }
+  __shared__ float2 sh[8][32];
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int y = 1; y < 8; ++y) { acc.x += sh[y][threadIdx.x].x; acc.y += sh[y][threadIdx.x].y; }
+    if (c < N) atomicAdd(out + c, acc.x);
+    if (c + 1 < N) atomicAdd(out + c + 1, acc.y);
+  }
+}
+
+// In-place NeoX-style RoPE on the first `rot_cols` columns of each row (blocks of 64: H query heads and
+// the shared key head).  x' = x cos + rotate_half(x) sin; `sign` = -1 applies the inverse rotation
+// (used for the gradient).  cs: (T, 32, 2) fp32 = (cos, sin) per position and frequency.
+__global__ void __launch_bounds__(NT) rope_kernel(bf16* __restrict__ qkv, long long M, int T, int ld, int rot_cols,
+                                                  const float* __restrict__ cs, float sign) {
+  const int pairs_per_row = rot_cols >> 1;  // (i, i+32) pairs: 32 per head
+  const long long total = M * pairs_per_row;
+  for (long long idx = (long long)blockIdx.x * NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
+    const long long row = idx / pairs_per_row;
+    const int p = (int)(idx - row * pairs_per_row);
+    const int head = p >> 5, i = p & 31;
+    const int t = (int)(row % T);
+    const float c = cs[(t * 32 + i) * 2], s = sign * cs[(t * 32 + i) * 2 + 1];
+    bf16* base = qkv + row * ld + head * 64;
+    const float x1 = __bfloat162float(base[i]), x2 = __bfloat162float(base[i + 32]);
+    base[i] = __float2bfloat16(x1 * c - x2 * s);
+    base[i + 32] = __float2bfloat16(x2 * c + x1 * s);
+  }
+}
+
+}  // namespace
+
+extern "C" int tasr_cast_f32_bf16(const float* in, void* out, int64_t n, float alpha, float drop_p, uint64_t seed,
+                                  tasr_stream_t stream) {
+  if (n <= 0) return TASR_OK;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7)) return TASR_ERR_ALIGN;
+  uint32_t thresh = 0;
+  float inv_keep = 1.f;
+  if (drop_p > 0.f) {
+    double t = (double)drop_p * 4294967296.0;
+    thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    if (thresh == 0) thresh = 1;
+    inv_keep = 1.f / (1.f - drop_p);
+  }
+  const int grid = (int)imin64((long long)148 * 8, ((n >> 2) + NT) / NT);
+  cast_f32_bf16_kernel<<<grid, NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, reinterpret_cast<bf16*>(out), n, alpha,
+                                                                                 thresh, inv_keep, seed);
+  TASR_CHECK_LAUNCH();
+  return TASR_OK;
+}
+
+extern "C" int tasr_colsum_bf16(const void* in, int64_t M, int N, int64_t ld, float* out, tasr_stream_t stream) {
+  if (M <= 0 || N <= 0 || (ld & 1)) return TASR_ERR_SHAPE;
+  const int col_blocks = cdiv(N, 64);
+  int row_blocks = (int)((M + 63) / 64);
+  if (row_blocks > 1184 / col_blocks) row_blocks = 1184 / col_blocks;
+  if (row_blocks < 1) row_blocks = 1;
+  const int rows_per_cta = (int)((M + row_blocks - 1) / row_blocks);
+  row_blocks = (int)((M + rows_per_cta - 1) / rows_per_cta);
+  dim3 grid(col_blocks, row_blocks), block(32, 8);
+  colsum_bf16_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(in), M, N,
+                                                                                 ld, rows_per_cta, out);
+  TASR_CHECK_LAUNCH();
+  return TASR_OK;
+}
+
+extern "C" int tasr_rope_inplace(void* qkv, int64_t M, int T, int ld, int rot_cols, const float* cos_sin, int inverse,
+                                 tasr_stream_t stream) {
+  if (rot_cols % 64 || M <= 0 || T <= 0) return TASR_ERR_SHAPE;
+  const long long total = M * (rot_cols / 2);
+  const int grid = (int)imin64((long long)148 * 8, (total + NT - 1) / NT);
+  rope_kernel<<<grid, NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<bf16*>(qkv), M, T, ld, rot_cols,
+                                                                       cos_sin, inverse ? -1.f : 1.f);
+  TASR_CHECK_LAUNCH();
+  return TASR_OK;
+}

@@ -1,0 +1,458 @@
+// GroupNorm over (channels-in-group x ALL padded time) per sample on token-major (B, T, d) tensors,
+// and BatchNorm1d(+SiLU) over (B*T) per channel, forward and backward.  HBM-bound kernels:
+// vectorised 16-byte accesses, warp-shuffle / shared-memory reductions, partials reduced in double.
+// Replaces (reference): model/conformer.py:45-49 TransposeGroupNorm.forward (2 transposes +
+//   native_group_norm) and its backward; :84-85 BatchNorm1d + SiLU in ConformerConvModule.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4_bf16(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4_bf16(bf16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---------------------------------------------------------------- GroupNorm forward
+// partial[b][chunk][G][2] = (sum, sumsq) over the chunk's rows
+__global__ void __launch_bounds__(NT) gn_stats_kernel(const float* __restrict__ x, int T, int d, int G, int rows_per_cta,
+                                                      float* __restrict__ partial) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tpr = d >> 2;             // threads per row
+  const int rlanes = NT / tpr;        // rows in flight
+  const int col = (threadIdx.x % tpr) << 2;
+  const int rl = threadIdx.x / tpr;
+  const int t0 = chunk * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
+  float s = 0.f, ss = 0.f;
+  for (int t = t0 + rl; t < t1; t += rlanes) {
+    float4 v = ld4(x + ((long long)b * T + t) * d + col);
+    s += (v.x + v.y) + (v.z + v.w);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  __shared__ float sh_s[NT], sh_ss[NT];
+  sh_s[threadIdx.x] = s;
+  sh_ss[threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int cpg = d / G, tpg = cpg >> 2;  // threads (float4 columns) per group
+    float a = 0.f, c = 0.f;
+    for (int r = 0; r < rlanes; ++r)
+      for (int j = 0; j < tpg; ++j) {
+        int idx = r * tpr + threadIdx.x * tpg + j;
+        a += sh_s[idx];
+        c += sh_ss[idx];
+      }
+    float* o = partial + (((long long)b * gridDim.x + chunk) * G + threadIdx.x) * 2;
+    o[0] = a;
+    o[1] = c;
+  }
+}
+
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(NT) gn_apply_kernel(const float* __restrict__ x, int T, int d, int G, int rows_per_cta,
+                                                      const float* __restrict__ partial, int nchunk_stats, float eps,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      void* __restrict__ out, float* __restrict__ stats_out) {
+  const int b = blockIdx.y;
+  __shared__ float sh_mean[64], sh_rstd[64];
+  if (threadIdx.x < G) {
+    double s = 0.0, ss = 0.0;
+    for (int c = 0; c < nchunk_stats; ++c) {
+      const float* p = partial + (((long long)b * nchunk_stats + c) * G + threadIdx.x) * 2;
+      s += p[0];
+      ss += p[1];
+    }
+    const double n = (double)T * (d / G);
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    sh_mean[threadIdx.x] = (float)mean;
+    sh_rstd[threadIdx.x] = rstd;
+    if (blockIdx.x == 0 && stats_out != nullptr) {
+      stats_out[((long long)b * G + threadIdx.x) * 2] = (float)mean;
+      stats_out[((long long)b * G + threadIdx.x) * 2 + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  const int tpr = d >> 2, rlanes = NT / tpr;
+  const int col = (threadIdx.x % tpr) << 2, rl = threadIdx.x / tpr;
+  const int g = col / (d / G);
+  const float mean = sh_mean[g], rstd = sh_rstd[g];
+  const float4 ga = ld4(gamma + col), be = ld4(beta + col);
+  const int t0 = blockIdx.x * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
+  for (int t = t0 + rl; t < t1; t += rlanes) {
+    const long long off = ((long long)b * T + t) * d + col;
+    float4 v = ld4(x + off);
+    v.x = (v.x - mean) * rstd * ga.x + be.x;
+    v.y = (v.y - mean) * rstd * ga.y + be.y;
+    v.z = (v.z - mean) * rstd * ga.z + be.z;
+    v.w = (v.w - mean) * rstd * ga.w + be.w;
+    if (OUT_BF16) st4_bf16(reinterpret_cast<bf16*>(out) + off, v);
+    else *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + off) = v;
+  }
+}
+
+// ---------------------------------------------------------------- GroupNorm backward
+// partial[b][chunk][d][2] = per-channel (sum dy*xhat, sum dy) over the chunk's rows
+template <bool DY_BF16>
+__global__ void __launch_bounds__(NT) gn_bwd_stats_kernel(const void* __restrict__ dy, const float* __restrict__ x, int T,
+                                                          int d, int G, int rows_per_cta, const float* __restrict__ stats,
+                                                          float* __restrict__ partial) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tpr = d >> 2, rlanes = NT / tpr;
+  const int col = (threadIdx.x % tpr) << 2, rl = threadIdx.x / tpr;
+  const int g = col / (d / G);
+  const float mean = stats[((long long)b * G + g) * 2], rstd = stats[((long long)b * G + g) * 2 + 1];
+  const int t0 = chunk * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
+  float4 a = make_float4(0, 0, 0, 0), c = make_float4(0, 0, 0, 0);
+  for (int t = t0 + rl; t < t1; t += rlanes) {
+    const long long off = ((long long)b * T + t) * d + col;
+    float4 xv = ld4(x + off);
+    float4 g4 = DY_BF16 ? ld4_bf16(reinterpret_cast<const bf16*>(dy) + off) : ld4(reinterpret_cast<const float*>(dy) + off);
+    a.x += g4.x * (xv.x - mean) * rstd; a.y += g4.y * (xv.y - mean) * rstd;
+    a.z += g4.z * (xv.z - mean) * rstd; a.w += g4.w * (xv.w - mean) * rstd;
+    c.x += g4.x; c.y += g4.y; c.z += g4.z; c.w += g4.w;
+  }
+  __shared__ float4 sh_a[NT], sh_c[NT];
+  sh_a[threadIdx.x] = a;
+  sh_c[threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.x < tpr) {
+    for (int r = 1; r < rlanes; ++r) {
+      float4 a2 = sh_a[r * tpr + threadIdx.x], c2 = sh_c[r * tpr + threadIdx.x];
+      a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w;
+      c.x += c2.x; c.y += c2.y; c.z += c2.z; c.w += c2.w;
+    }
+    float* o = partial + (((long long)b * gridDim.x + chunk) * d + col) * 2;
+    o[0] = a.x; o[1] = c.x; o[2] = a.y; o[3] = c.y; o[4] = a.z; o[5] = c.z; o[6] = a.w; o[7] = c.w;
+  }
+}
+
+// dx = rstd * (dy*gamma - S1/n - xhat*S2/n);  dres_out = (accumulate ? dres_in : 0) + dx
+template <bool DY_BF16>
+__global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const void* __restrict__ dy, const float* __restrict__ x, int T,
+                                                          int d, int G, int rows_per_cta, const float* __restrict__ stats,
+                                                          const float* __restrict__ partial, int nchunk_stats,
+                                                          const float* __restrict__ gamma, float* __restrict__ dres,
+                                                          int accumulate, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta) {
+  const int b = blockIdx.y;
+  extern __shared__ float sh_dyn[];  // d floats: a_c ; d floats: c_c ; G: S1 ; G: S2
+  float* sh_a = sh_dyn;
+  float* sh_c = sh_dyn + d;
+  float* sh_s1 = sh_c + d;
+  float* sh_s2 = sh_s1 + G;
+  for (int ch = threadIdx.x; ch < d; ch += NT) {
+    double a = 0.0, c = 0.0;
+    for (int k = 0; k < nchunk_stats; ++k) {
+      const float* p = partial + (((long long)b * nchunk_stats + k) * d + ch) * 2;
+      a += p[0];
+      c += p[1];
+    }
+    sh_a[ch] = (float)a;
+    sh_c[ch] = (float)c;
+    if (blockIdx.x == 0) {
+      if (dgamma) atomicAdd(dgamma + ch, (float)a);
+      if (dbeta) atomicAdd(dbeta + ch, (float)c);
+    }
+  }
+  __syncthreads();
+  const int cpg = d / G;
+  if (threadIdx.x < G) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      const int ch = threadIdx.x * cpg + j;
+      s1 += gamma[ch] * sh_c[ch];
+      s2 += gamma[ch] * sh_a[ch];
+    }
+    const float inv_n = 1.f / ((float)T * cpg);
+    sh_s1[threadIdx.x] = s1 * inv_n;
+    sh_s2[threadIdx.x] = s2 * inv_n;
+  }
+  __syncthreads();
+  const int tpr = d >> 2, rlanes = NT / tpr;
+  const int col = (threadIdx.x % tpr) << 2, rl = threadIdx.x / tpr;
+  const int g = col / cpg;
+  const float mean = stats[((long long)b * G + g) * 2], rstd = stats[((long long)b * G + g) * 2 + 1];
+  const float s1 = sh_s1[g], s2 = sh_s2[g];
+  const float4 ga = ld4(gamma + col);
+  const int t0 = blockIdx.x * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
+  for (int t = t0 + rl; t < t1; t += rlanes) {
+    const long long off = ((long long)b * T + t) * d + col;
+    float4 xv = ld4(x + off);
+    float4 g4 = DY_BF16 ? ld4_bf16(reinterpret_cast<const bf16*>(dy) + off) : ld4(reinterpret_cast<const float*>(dy) + off);
+    float4 r;
+    r.x = rstd * (g4.x * ga.x - s1 - (xv.x - mean) * rstd * s2);
+    r.y = rstd * (g4.y * ga.y - s1 - (xv.y - mean) * rstd * s2);
+    r.z = rstd * (g4.z * ga.z - s1 - (xv.z - mean) * rstd * s2);
+    r.w = rstd * (g4.w * ga.w - s1 - (xv.w - mean) * rstd * s2);
+    if (accumulate) {
+      float4 o = ld4(dres + off);
+      r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+    }
+    *reinterpret_cast<float4*>(dres + off) = r;
+  }
+}
+
+// ---------------------------------------------------------------- BatchNorm (+SiLU)
+// reduce partial[npart][d][2] (sum, sumsq) -> mean / rstd; update running stats (training)
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int npart, int d, long long count, float eps,
+                                   float momentum, int training, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
+                                   float* __restrict__ stats) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= d) return;
+  const int ch = warp;
+  if (training) {
+    double s = 0.0, ss = 0.0;
+    for (int k = lane; k < npart; k += 32) {
+      const float* p = partial + ((long long)k * d + ch) * 2;
+      s += p[0];
+      ss += p[1];
+    }
+    s = warp_sum_d(s);
+    ss = warp_sum_d(ss);
+    if (lane == 0) {
+      const double mean = s / (double)count;
+      double var = ss / (double)count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[ch * 2] = (float)mean;
+      stats[ch * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+      if (running_mean) {
+        const double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+        running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
+        running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+      }
+      if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    }
+  } else if (lane == 0) {
+    stats[ch * 2] = running_mean[ch];
+    stats[ch * 2 + 1] = rsqrtf(running_var[ch] + eps);
+  }
+}
+
+// s = silu((w - mean) * rstd * gamma + beta)
+__global__ void __launch_bounds__(NT) bn_silu_apply_kernel(const bf16* __restrict__ w, long long M, int d,
+                                                           const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, bf16* __restrict__ out) {
+  const long long n4 = M * d / 4;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
+    const int col = (int)((i * 4) % d);
+    float4 v = ld4_bf16(w + i * 4);
+    float4 st0 = ld4(stats + col * 2), st1 = ld4(stats + col * 2 + 4);  // (m0,r0,m1,r1),(m2,r2,m3,r3)
+    float4 ga = ld4(gamma + col), be = ld4(beta + col);
+    v.x = siluf_((v.x - st0.x) * st0.y * ga.x + be.x);
+    v.y = siluf_((v.y - st0.z) * st0.w * ga.y + be.y);
+    v.z = siluf_((v.z - st1.x) * st1.y * ga.z + be.z);
+    v.w = siluf_((v.w - st1.z) * st1.w * ga.w + be.w);
+    st4_bf16(out + i * 4, v);
+  }
+}
+
+// backward pass 1: per-channel partial sums of dz*what and dz  (dz = ds * silu'(z))
+__global__ void __launch_bounds__(NT) bn_silu_bwd_stats_kernel(const bf16* __restrict__ ds, const bf16* __restrict__ w,
+                                                               long long M, int d, int rows_per_cta,
+                                                               const float* __restrict__ stats,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float* __restrict__ partial) {
+  const int tpr = d >> 2, rlanes = NT / tpr;
+  const int col = (threadIdx.x % tpr) << 2, rl = threadIdx.x / tpr;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(M, r0 + (long long)rows_per_cta);
+  float mean[4], rstd[4], ga[4], be[4];
+  for (int j = 0; j < 4; ++j) {
+    mean[j] = stats[(col + j) * 2]; rstd[j] = stats[(col + j) * 2 + 1];
+    ga[j] = gamma[col + j]; be[j] = beta[col + j];
+  }
+  float a[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+  for (long long r = r0 + rl; r < r1; r += rlanes) {
+    float4 wv = ld4_bf16(w + r * d + col), dv = ld4_bf16(ds + r * d + col);
+    const float wq[4] = {wv.x, wv.y, wv.z, wv.w}, dq[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float wh = (wq[j] - mean[j]) * rstd[j];
+      const float dz = dq[j] * silu_gradf_(wh * ga[j] + be[j]);
+      a[j] += dz * wh;
+      c[j] += dz;
+    }
+  }
+  __shared__ float sh[NT][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sh[threadIdx.x][j] = a[j]; sh[threadIdx.x][4 + j] = c[j]; }
+  __syncthreads();
+  if (threadIdx.x < tpr) {
+    for (int r = 1; r < rlanes; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j] += sh[r * tpr + threadIdx.x][j]; c[j] += sh[r * tpr + threadIdx.x][4 + j]; }
+    float* o = partial + ((long long)blockIdx.x * d + col) * 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[2 * j] = a[j]; o[2 * j + 1] = c[j]; }
+  }
+}
+// reduce partials -> sums[d][2]; accumulate dgamma / dbeta
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int npart, int d, float* __restrict__ sums,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= d) return;
+  double a = 0.0, c = 0.0;
+  for (int k = lane; k < npart; k += 32) {
+    const float* p = partial + ((long long)k * d + warp) * 2;
+    a += p[0];
+    c += p[1];
+  }
+  a = warp_sum_d(a);
+  c = warp_sum_d(c);
+  if (lane == 0) {
+    sums[warp * 2] = (float)a;
+    sums[warp * 2 + 1] = (float)c;
+    if (dgamma) atomicAdd(dgamma + warp, (float)a);
+    if (dbeta) atomicAdd(dbeta + warp, (float)c);
+  }
+}
+// dw = gamma*rstd*(dz - C/M - what*A/M)
+__global__ void __launch_bounds__(NT) bn_silu_bwd_apply_kernel(const bf16* __restrict__ ds, const bf16* __restrict__ w,
+                                                               long long M, int d, const float* __restrict__ stats,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               const float* __restrict__ sums, bf16* __restrict__ dw) {
+  const long long n4 = M * d / 4;
+  const float invM = 1.f / (float)M;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
+    const int col = (int)((i * 4) % d);
+    float4 wv = ld4_bf16(w + i * 4), dv = ld4_bf16(ds + i * 4);
+    const float wq[4] = {wv.x, wv.y, wv.z, wv.w}, dq[4] = {dv.x, dv.y, dv.z, dv.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float mean = stats[(col + j) * 2], rstd = stats[(col + j) * 2 + 1];
+      const float ga = gamma[col + j], be = beta[col + j];
+      const float wh = (wq[j] - mean) * rstd;
+      const float dz = dq[j] * silu_gradf_(wh * ga + be);
+      o[j] = ga * rstd * (dz - sums[(col + j) * 2 + 1] * invM - wh * sums[(col + j) * 2] * invM);
+    }
+    st4_bf16(dw + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+bool gn_shape_ok(int d, int G) {
+  if (d <= 0 || G <= 0 || G > 64 || d % G) return false;
+  const int cpg = d / G;
+  if (cpg % 4) return false;
+  const int tpr = d / 4;
+  return tpr <= NT && (NT % tpr) == 0;
+}
+int gn_rows_per_cta(int B, int T) {
+  int chunks = max(1, 296 / max(B, 1));
+  int rows = cdiv(T, chunks);
+  return max(rows, 8);
+}
+
+}  // namespace
+
+extern "C" int tasr_groupnorm_chunks(int B, int T) { return cdiv(T, gn_rows_per_cta(B, T)); }
+
+extern "C" size_t tasr_groupnorm_workspace_bytes(int B, int T, int d) {
+  return (size_t)B * tasr_groupnorm_chunks(B, T) * d * 2 * sizeof(float);
+}
+
+extern "C" int tasr_groupnorm_fwd(const float* x, int B, int T, int d, int G, float eps, const float* gamma,
+                                  const float* beta, void* out, int out_bf16, float* stats, void* workspace,
+                                  size_t workspace_bytes, tasr_stream_t stream) {
+  if (!gn_shape_ok(d, G) || B <= 0 || T <= 0) return TASR_ERR_SHAPE;
+  if (workspace_bytes < tasr_groupnorm_workspace_bytes(B, T, d)) return TASR_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rows = gn_rows_per_cta(B, T), nchunk = cdiv(T, rows);
+  float* partial = reinterpret_cast<float*>(workspace);
+  dim3 grid(nchunk, B);
+  gn_stats_kernel<<<grid, NT, 0, st>>>(x, T, d, G, rows, partial);
+  TASR_CHECK_LAUNCH();
+  if (out_bf16) gn_apply_kernel<true><<<grid, NT, 0, st>>>(x, T, d, G, rows, partial, nchunk, eps, gamma, beta, out, stats);
+  else gn_apply_kernel<false><<<grid, NT, 0, st>>>(x, T, d, G, rows, partial, nchunk, eps, gamma, beta, out, stats);
+  TASR_CHECK_LAUNCH();
+  return TASR_OK;
+}
+
+extern "C" int tasr_groupnorm_bwd(const void* dy, int dy_bf16, const float* x, int B, int T, int d, int G,
+                                  const float* stats, const float* gamma, float* dres, int accumulate, float* dgamma,
+                                  float* dbeta, void* workspace, size_t workspace_bytes, tasr_stream_t stream) {
+  if (!gn_shape_ok(d, G) || B <= 0 || T <= 0) return TASR_ERR_SHAPE;
+  if (workspace_bytes < tasr_groupnorm_workspace_bytes(B, T, d)) return TASR_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rows = gn_rows_per_cta(B, T), nchunk = cdiv(T, rows);
+  float* partial = reinterpret_cast<float*>(workspace);
+  dim3 grid(nchunk, B);
+  const size_t sm = (size_t)(2 * d + 2 * G) * sizeof(float);
+  if (dy_bf16) {
+    gn_bwd_stats_kernel<true><<<grid, NT, 0, st>>>(dy, x, T, d, G, rows, stats, partial);
+    TASR_CHECK_LAUNCH();
+    gn_bwd_apply_kernel<true><<<grid, NT, sm, st>>>(dy, x, T, d, G, rows, stats, partial, nchunk, gamma, dres, accumulate,
+                                                    dgamma, dbeta);
+  } else {
+    gn_bwd_stats_kernel<false><<<grid, NT, 0, st>>>(dy, x, T, d, G, rows, stats, partial);
+    TASR_CHECK_LAUNCH();
+    gn_bwd_apply_kernel<false><<<grid, NT, sm, st>>>(dy, x, T, d, G, rows, stats, partial, nchunk, gamma, dres, accumulate,
+                                                     dgamma, dbeta);
+  }
+  TASR_CHECK_LAUNCH();
+  return TASR_OK;
+}
+
+// ---- BatchNorm + SiLU
+extern "C" int tasr_bn_finalize(const float* partial, int npart, int d, int64_t count, float eps, float momentum,
+                                int training, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                float* stats, tasr_stream_t stream) {
+  if (d <= 0 || (training && npart <= 0)) return TASR_ERR_SHAPE;
+  bn_finalize_kernel<<<cdiv((long long)d * 32, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial, npart, d, count, eps, momentum, training, running_mean, running_var,
+      reinterpret_cast<long long*>(num_batches_tracked), stats);
+  TASR_CHECK_LAUNCH();
+  return TASR_OK;
+}
+
+extern "C" int tasr_bn_silu_fwd(const void* w, int64_t M, int d, const float* stats, const float* gamma,
+                                const float* beta, void* out, tasr_stream_t stream) {
+  if (d % 4 || M <= 0) return TASR_ERR_SHAPE;
+  const int grid = (int)imin64((long long)148 * 8, (M * d / 4 + NT - 1) / NT);
+  bn_silu_apply_kernel<<<grid, NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(w), M, d, stats, gamma, beta, reinterpret_cast<bf16*>(out));
+  TASR_CHECK_LAUNCH();
+  return TASR_OK;
+}
+
+extern "C" int tasr_bn_bwd_parts(int64_t M) { return (int)imin64((long long)296, (long long)((M + 31) / 32)); }
+
+extern "C" size_t tasr_bn_bwd_workspace_bytes(int64_t M, int d) {
+  return ((size_t)tasr_bn_bwd_parts(M) * d * 2 + (size_t)d * 2) * sizeof(float);
+}
+
+extern "C" int tasr_bn_silu_bwd(const void* ds, const void* w, int64_t M, int d, const float* stats,
+                                const float* gamma, const float* beta, void* dw, float* dgamma, float* dbeta,
+                                void* workspace, size_t workspace_bytes, tasr_stream_t stream) {
+  const int tpr = d / 4;
+  if (d % 4 || tpr > NT || (NT % tpr) || M <= 0) return TASR_ERR_SHAPE;
+  if (workspace_bytes < tasr_bn_bwd_workspace_bytes(M, d)) return TASR_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nparts_max = tasr_bn_bwd_parts(M);
+  const int rows = (int)((M + nparts_max - 1) / nparts_max);
+  const int nparts = (int)((M + rows - 1) / rows);
+  float* partial = reinterpret_cast<float*>(workspace);
+  float* sums = partial + (size_t)nparts_max * d * 2;
+  bn_silu_bwd_stats_kernel<<<nparts, NT, 0, st>>>(reinterpret_cast<const bf16*>(ds), reinterpret_cast<const bf16*>(w), M, d,
+                                                  rows, stats, gamma, beta, partial);
+  TASR_CHECK_LAUNCH();
+  bn_bwd_finalize_kernel<<<cdiv((long long)d * 32, 256), 256, 0, st>>>(partial, nparts, d, sums, dgamma, dbeta);
+  TASR_CHECK_LAUNCH();
+  const int grid = (int)imin64((long long)148 * 8, (M * d / 4 + NT - 1) / NT);
+  bn_silu_bwd_apply_kernel<<<grid, NT, 0, st>>>(reinterpret_cast<const bf16*>(ds), reinterpret_cast<const bf16*>(w), M, d,
+                                                stats, gamma, beta, sums, reinterpret_cast<bf16*>(dw));
+  TASR_CHECK_LAUNCH();
+  return TASR_OK;
+}
