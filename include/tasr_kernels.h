@@ -209,13 +209,13 @@ int tasr_pack_weight_remap(const float* in, int64_t N, int K, int q, void* out, 
 /* ------------------------------------------------------------------------------------------------
  * Fused log-softmax + CTC loss (mean reduction, zero_infinity) + gradient w.r.t. the logits.
  * Replaces: trainer/trainer.py:167-173 (log_softmax + nn.CTCLoss(blank=0, zero_infinity=True)) and
- *   their backward.  logits (B,T,V) bf16 or fp32; targets (B,Smax) int64 padded; lengths int64 (B),
+ *   their backward.  logits (B,T,V) bf16 or fp32 with row pitch ld >= V elements (dlogits: same pitch); targets (B,Smax) int64 padded; lengths int64 (B),
  *   all on the device.  loss (1) fp32 = mean_b(nll_b / max(S_b,1)), infeasible samples contribute 0;
  *   nll (B) fp32 or NULL; dlogits same dtype/shape as logits (or NULL) =
  *   grad_scale * (softmax - occupancy) / (B * max(S_b,1)) for t < input_lengths[b], else 0.
  * ---------------------------------------------------------------------------------------------- */
 size_t tasr_ctc_workspace_bytes(int B, int T, int V, int Smax);
-int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int B, int T, int V, const int64_t* targets, int Smax,
+int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int64_t ld, int B, int T, int V, const int64_t* targets, int Smax,
                           const int64_t* input_lengths, const int64_t* target_lengths, int blank, float grad_scale,
                           float* loss, float* nll, void* dlogits, void* workspace, size_t workspace_bytes,
                           tasr_stream_t stream);
@@ -235,7 +235,7 @@ int tasr_clip_adamw(float* p, const float* g, float* m, float* v, void* shadow_b
  *   ids (B,T) int64 argmax; tokens (B,T) int64 collapsed (repeats merged, blanks dropped, -1 padded);
  *   out_len (B) int32.  lengths (B) int64 or NULL = frames to decode per utterance.
  * ---------------------------------------------------------------------------------------------- */
-int tasr_argmax_collapse(const void* logits, int logits_bf16, int B, int T, int V, const int64_t* lengths, int blank,
+int tasr_argmax_collapse(const void* logits, int logits_bf16, int64_t ld, int B, int T, int V, const int64_t* lengths, int blank,
                          int64_t* ids, int64_t* tokens, int32_t* out_len, tasr_stream_t stream);
 
 #ifdef __cplusplus

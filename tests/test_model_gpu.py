@@ -1,0 +1,103 @@
+"""End-to-end parity of the drop-in TurkishASRModel (B200 kernels, bf16 operands) against the fp32 CPU
+oracle (oracle/conformer.py) on identical synthetic inputs and weights.
+
+Tolerances from BASELINE.json north_star: encoder logits 2e-2 relative (bf16 mode), CTC loss 1e-3
+relative given the same logits, gradients compared at bf16 resolution."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import conformer as oc
+from turkish_asr_model_b200 import _lib as L
+from turkish_asr_model_b200.model import TurkishASRModel
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(cuda, d=256, H=4, nb=2, V=100, B=3, T=203, seed=0):
+    torch.manual_seed(seed)
+    model = TurkishASRModel(80, d, H, nb, V, dropout=0.0)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, T, 80, generator=g)
+    il = torch.tensor([T, max(T - 53, 8), max(T // 2, 8)][:B])
+    for b in range(B):
+        x[b, il[b]:] = 0.0
+    return model.to(cuda).train(), sd, x, il
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+def test_state_dict_layout_and_flat_params(cuda):
+    model, sd, x, il = _make(cuda)
+    keys = list(model.state_dict().keys())
+    assert keys == list(sd.keys())
+    assert "blocks.0.norm_conv.norm.weight" in keys and "blocks.0.attn.rotary_emb.inv_freq" in keys
+    assert "blocks.0.conv.batch_norm.num_batches_tracked" in keys
+    model(x.to(cuda), il)  # flattens
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]) or k.endswith(("running_mean", "running_var", "num_batches_tracked")), k
+
+
+@pytest.mark.parametrize("masked", [True, False])
+def test_forward_logits_parity(cuda, masked):
+    model, sd, x, il = _make(cuda)
+    lengths = il if masked else None
+    ref = oc.forward(x, lengths, sd, 4, 2, training=True)
+    out = model(x.to(cuda), lengths)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape == (3, oc.encoder_frames(203), 100)
+    assert _rel(out, ref) < 2e-2
+    # BatchNorm running statistics were updated like the reference does in train mode
+    bn_state = {}
+    oc.forward(x, lengths, sd, 4, 2, training=True, bn_state=bn_state)
+    for k, v in bn_state.items():
+        assert _rel(model.state_dict()[k], v) < 2e-2, k
+
+
+def test_eval_forward_parity(cuda):
+    model, sd, x, il = _make(cuda)
+    model.eval()
+    with torch.no_grad():
+        out = model(x.to(cuda), il)
+    ref = oc.forward(x, il, sd, 4, 2, training=False)
+    assert _rel(out, ref) < 2e-2
+
+
+def test_backward_parity(cuda):
+    model, sd, x, il = _make(cuda)
+    B, V = 3, 100
+    g = torch.Generator().manual_seed(5)
+    targets = torch.randint(1, V, (B, 10), generator=g)
+    tl = torch.tensor([10, 7, 4])
+    # oracle: fp32 autograd through the functional restatement + torch CTC (the reference's own loss call)
+    pnames = {n for n, _ in model.named_parameters()}
+    sdr = {k: (v.clone().requires_grad_(True) if k in pnames else v) for k, v in sd.items()}
+    logits_ref = oc.forward(x, il, sdr, 4, 2, training=True)
+    loss_ref = oc.ctc_loss_torch(logits_ref, targets, il, tl)
+    loss_ref.backward()
+    # device
+    logits = model(x.to(cuda), il)
+    loss, nll, dlogits = L.ctc_loss_fwd_bwd(logits.detach(), targets.to(cuda), (il // 4).to(cuda), tl.to(cuda))
+    logits.backward(dlogits)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    worst = {}
+    for name, p in model.named_parameters():
+        gref = sdr[name].grad
+        if gref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name  # dead norm_conv params
+            continue
+        assert p.grad is not None, name
+        if name.endswith("depthwise_conv.bias"):
+            # a bias in front of BatchNorm has an exactly-zero gradient; both sides only hold rounding noise
+            wg = dict(model.named_parameters())[name.replace(".bias", ".weight")].grad
+            assert float(p.grad.abs().max()) < 1e-2 * float(wg.abs().max()), name
+            continue
+        worst[name] = _rel(p.grad, gref)
+    bad = {k: v for k, v in worst.items() if v > 6e-2}
+    assert not bad, bad
+    assert np.median(list(worst.values())) < 2e-2

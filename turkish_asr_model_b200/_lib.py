@@ -45,10 +45,10 @@ _SIGNATURES = {
     "tasr_col2im_conv1_bwd": (I, [P, P, I, I, I, I, P, P, P, P, P]),
     "tasr_pack_weight_remap": (I, [P, L, I, I, P, P]),
     "tasr_ctc_workspace_bytes": (Z, [I, I, I, I]),
-    "tasr_ctc_loss_fwd_bwd": (I, [P, I, I, I, I, P, I, P, P, I, F, P, P, P, P, Z, P]),
+    "tasr_ctc_loss_fwd_bwd": (I, [P, I, L, I, I, I, P, I, P, P, I, F, P, P, P, P, Z, P]),
     "tasr_grad_sumsq": (I, [P, L, P, P]),
     "tasr_clip_adamw": (I, [P, P, P, P, P, L, P, P, P, P]),
-    "tasr_argmax_collapse": (I, [P, I, I, I, I, P, I, P, P, P, P]),
+    "tasr_argmax_collapse": (I, [P, I, L, I, I, I, P, I, P, P, P, P]),
 }
 
 
@@ -334,17 +334,31 @@ def pack_weight_remap(w2d, q):
 # ---------------------------------------------------------------------------------------------
 # CTC, optimizer, decode
 # ---------------------------------------------------------------------------------------------
+def _rows_view(logits):
+    """(B,T,V) tensor whose rows are dense with a common pitch ld >= V -> (tensor, ld); copies otherwise."""
+    B, T, V = logits.shape
+    if logits.stride(2) == 1 and logits.stride(0) == T * logits.stride(1) and logits.stride(1) >= V:
+        return logits, logits.stride(1)
+    logits = logits.contiguous()
+    return logits, V
+
+
 def ctc_loss_fwd_bwd(logits, targets, input_lengths, target_lengths, blank=0, grad_scale=1.0, want_grad=True):
     """logits (B,T,V) bf16|fp32; targets (B,Smax) int64; lengths int64 (device) -> (loss (1), nll (B), dlogits)."""
     require_cuda(logits, targets, input_lengths, target_lengths)
     B, T, V = logits.shape
+    logits, ld = _rows_view(logits)
     Smax = targets.shape[1]
     loss = torch.empty(1, dtype=torch.float32, device=logits.device)
     nll = torch.empty(B, dtype=torch.float32, device=logits.device)
-    dlogits = torch.empty_like(logits) if want_grad else None
+    dlogits = None
+    if want_grad:  # same row pitch as the logits; padding columns (if any) are zero
+        dl = torch.zeros(B * T, ld, dtype=logits.dtype, device=logits.device) if ld != V else \
+            torch.empty(B * T, ld, dtype=logits.dtype, device=logits.device)
+        dlogits = dl.view(B, T, ld)[:, :, :V]
     wsb = lib().tasr_ctc_workspace_bytes(B, T, V, Smax)
     ws = workspace(wsb, logits.device)
-    check(lib().tasr_ctc_loss_fwd_bwd(ptr(logits), int(logits.dtype == torch.bfloat16), B, T, V, ptr(targets), Smax,
+    check(lib().tasr_ctc_loss_fwd_bwd(ptr(logits), int(logits.dtype == torch.bfloat16), ld, B, T, V, ptr(targets), Smax,
                                       ptr(input_lengths), ptr(target_lengths), blank, grad_scale, ptr(loss), ptr(nll),
                                       ptr(dlogits), ptr(ws), wsb, stream_ptr()))
     return loss, nll, dlogits
@@ -362,9 +376,10 @@ def clip_adamw(p, g, m, v, shadow, hyper, sumsq, norm_out):
 def argmax_collapse(logits, lengths=None, blank=0):
     require_cuda(logits)
     B, T, V = logits.shape
+    logits, ld = _rows_view(logits)
     ids = torch.empty(B, T, dtype=torch.int64, device=logits.device)
     tokens = torch.empty(B, T, dtype=torch.int64, device=logits.device)
     out_len = torch.empty(B, dtype=torch.int32, device=logits.device)
-    check(lib().tasr_argmax_collapse(ptr(logits), int(logits.dtype == torch.bfloat16), B, T, V, ptr(lengths), blank,
+    check(lib().tasr_argmax_collapse(ptr(logits), int(logits.dtype == torch.bfloat16), ld, B, T, V, ptr(lengths), blank,
                                      ptr(ids), ptr(tokens), ptr(out_len), stream_ptr()))
     return ids, tokens, out_len

@@ -36,7 +36,7 @@ template <>
 __device__ __forceinline__ float ldlogit<bf16>(const bf16* p, long long i) { return __bfloat162float(p[i]); }
 
 template <typename TL>
-__global__ void __launch_bounds__(256) ctc_rowstats_kernel(const TL* __restrict__ logits, int B, int T, int V,
+__global__ void __launch_bounds__(256) ctc_rowstats_kernel(const TL* __restrict__ logits, long long ld, int B, int T, int V,
                                                            const long long* __restrict__ targets, int Smax,
                                                            const long long* __restrict__ in_len,
                                                            const long long* __restrict__ tgt_len, int blank,
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) ctc_rowstats_kernel(const TL* __restrict_
   const int b = warp / T, t = warp - b * T;
   const int L = (int)min((long long)T, in_len[b]);
   if (t >= L) return;
-  const TL* row = logits + ((long long)b * T + t) * V;
+  const TL* row = logits + ((long long)b * T + t) * ld;
   float m = NEG_INF;
   for (int c = lane; c < V; c += 32) m = fmaxf(m, ldlogit(row, c));
   m = warp_max(m);
@@ -165,7 +165,7 @@ template <>
 __device__ __forceinline__ void store_grad<bf16, bf16>(bf16* p, long long i, float v) { p[i] = __float2bfloat16(v); }
 
 template <typename TL>
-__global__ void __launch_bounds__(256) ctc_grad_kernel(const TL* __restrict__ logits, int B, int T, int V, int Smax,
+__global__ void __launch_bounds__(256) ctc_grad_kernel(const TL* __restrict__ logits, long long ld, int B, int T, int V, int Smax,
                                                        const long long* __restrict__ in_len,
                                                        const long long* __restrict__ tgt_len,
                                                        const float* __restrict__ lse_in, const float* __restrict__ lp,
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const TL* __restrict__ lo
   const int L = (int)min((long long)T, in_len[b]);
   const int S = (int)tgt_len[b];
   const float nll = nll_in[b];
-  TL* drow = dlogits + ((long long)b * T + t) * V;
+  TL* drow = dlogits + ((long long)b * T + t) * ld;
   if (t >= L || nll == INFINITY || nll != nll) {
     for (int c = lane; c < V; c += 32) store_grad<TL, TL>(drow, c, 0.f);
     return;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const TL* __restrict__ lo
   __syncwarp();
   const float scale = grad_scale / ((float)B * (float)max(S, 1));
   const float lse = lse_in[(long long)b * T + t];
-  const TL* row = logits + ((long long)b * T + t) * V;
+  const TL* row = logits + ((long long)b * T + t) * ld;
   const unsigned short* slots = slot_of_class + (long long)b * V;
   for (int c = lane; c < V; c += 32) {
     float v = expf(ldlogit(row, c) - lse);
@@ -236,11 +236,11 @@ extern "C" size_t tasr_ctc_workspace_bytes(int B, int T, int V, int Smax) {
   return n + 256;
 }
 
-extern "C" int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int B, int T, int V, const int64_t* targets,
+extern "C" int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int64_t ld, int B, int T, int V, const int64_t* targets,
                                      int Smax, const int64_t* input_lengths, const int64_t* target_lengths, int blank,
                                      float grad_scale, float* loss, float* nll, void* dlogits, void* workspace,
                                      size_t workspace_bytes, tasr_stream_t stream) {
-  if (B <= 0 || T <= 0 || V <= 0 || Smax < 0 || V > 65535) return TASR_ERR_SHAPE;
+  if (B <= 0 || T <= 0 || V <= 0 || Smax < 0 || V > 65535 || ld < V) return TASR_ERR_SHAPE;
   const int NSP = nsp_for(Smax);
   if (2 * NSP > 1024) return TASR_ERR_SHAPE;  // target length <= 255
   if (workspace_bytes < tasr_ctc_workspace_bytes(B, T, V, Smax)) return TASR_ERR_WORKSPACE;
@@ -263,10 +263,10 @@ extern "C" int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int B,
   const int rows = B * T;
   const int grid_rows = cdiv((long long)rows * 32, 256);
   if (logits_bf16)
-    ctc_rowstats_kernel<bf16><<<grid_rows, 256, 0, st>>>(reinterpret_cast<const bf16*>(logits), B, T, V, tg, Smax, il, tl,
+    ctc_rowstats_kernel<bf16><<<grid_rows, 256, 0, st>>>(reinterpret_cast<const bf16*>(logits), ld, B, T, V, tg, Smax, il, tl,
                                                          blank, lse, lp);
   else
-    ctc_rowstats_kernel<float><<<grid_rows, 256, 0, st>>>(reinterpret_cast<const float*>(logits), B, T, V, tg, Smax, il, tl,
+    ctc_rowstats_kernel<float><<<grid_rows, 256, 0, st>>>(reinterpret_cast<const float*>(logits), ld, B, T, V, tg, Smax, il, tl,
                                                           blank, lse, lp);
   TASR_CHECK_LAUNCH();
   float* nll_dst = nll != nullptr ? nll : nll_ws;
@@ -276,11 +276,11 @@ extern "C" int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int B,
   if (dlogits != nullptr) {
     const size_t sm = (size_t)8 * (Smax + 1) * sizeof(float);
     if (logits_bf16)
-      ctc_grad_kernel<bf16><<<grid_rows, 256, sm, st>>>(reinterpret_cast<const bf16*>(logits), B, T, V, Smax, il, tl, lse, lp,
+      ctc_grad_kernel<bf16><<<grid_rows, 256, sm, st>>>(reinterpret_cast<const bf16*>(logits), ld, B, T, V, Smax, il, tl, lse, lp,
                                                         alpha, beta, nll_dst, slots, first_occ, grad_scale,
                                                         reinterpret_cast<bf16*>(dlogits));
     else
-      ctc_grad_kernel<float><<<grid_rows, 256, sm, st>>>(reinterpret_cast<const float*>(logits), B, T, V, Smax, il, tl, lse,
+      ctc_grad_kernel<float><<<grid_rows, 256, sm, st>>>(reinterpret_cast<const float*>(logits), ld, B, T, V, Smax, il, tl, lse,
                                                          lp, alpha, beta, nll_dst, slots, first_occ, grad_scale,
                                                          reinterpret_cast<float*>(dlogits));
     TASR_CHECK_LAUNCH();

@@ -14,12 +14,12 @@ template <>
 __device__ __forceinline__ float ldv<bf16>(const bf16* p, long long i) { return __bfloat162float(p[i]); }
 
 template <typename TL>
-__global__ void __launch_bounds__(256) argmax_kernel(const TL* __restrict__ logits, long long rows, int V,
+__global__ void __launch_bounds__(256) argmax_kernel(const TL* __restrict__ logits, long long ld, long long rows, int V,
                                                      long long* __restrict__ ids) {
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  const TL* row = logits + warp * V;
+  const TL* row = logits + warp * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
   for (int c = lane; c < V; c += 32) {
@@ -77,16 +77,16 @@ __global__ void __launch_bounds__(256) collapse_kernel(const long long* __restri
 }  // namespace
 
 // ids (B, T) int64: per-frame argmax; tokens (B, T) int64: collapsed ids, padded with -1; out_len (B) int32
-extern "C" int tasr_argmax_collapse(const void* logits, int logits_bf16, int B, int T, int V, const int64_t* lengths,
+extern "C" int tasr_argmax_collapse(const void* logits, int logits_bf16, int64_t ld, int B, int T, int V, const int64_t* lengths,
                                     int blank, int64_t* ids, int64_t* tokens, int32_t* out_len, tasr_stream_t stream) {
-  if (B <= 0 || T <= 0 || V <= 0) return TASR_ERR_SHAPE;
+  if (B <= 0 || T <= 0 || V <= 0 || ld < V) return TASR_ERR_SHAPE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long rows = (long long)B * T;
   if (logits_bf16)
-    argmax_kernel<bf16><<<cdiv(rows * 32, 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(logits), rows, V,
+    argmax_kernel<bf16><<<cdiv(rows * 32, 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(logits), ld, rows, V,
                                                               reinterpret_cast<long long*>(ids));
   else
-    argmax_kernel<float><<<cdiv(rows * 32, 256), 256, 0, st>>>(reinterpret_cast<const float*>(logits), rows, V,
+    argmax_kernel<float><<<cdiv(rows * 32, 256), 256, 0, st>>>(reinterpret_cast<const float*>(logits), ld, rows, V,
                                                                reinterpret_cast<long long*>(ids));
   TASR_CHECK_LAUNCH();
   if (tokens != nullptr) {
