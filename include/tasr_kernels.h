@@ -41,6 +41,8 @@ const char* tasr_last_error(void);
 int tasr_version(void);
 /* 0 when the current device is compute capability 10.x, TASR_ERR_ARCH otherwise. */
 int tasr_check_device(void);
+/* number of CUDA kernels this library has launched in this process (monotonic). */
+uint64_t tasr_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contractions on tcgen05 / TMEM (bf16 in, fp32 accumulate), operands staged by TMA.

@@ -20,6 +20,7 @@ _SIGNATURES = {
     "tasr_version": (I, []),
     "tasr_check_device": (I, []),
     "tasr_init": (I, []),
+    "tasr_launch_count": (U64, []),
     "tasr_gemm_bf16": (I, [P, P]),
     "tasr_gemm_bf16_debug": (I, [P, P]),
     "tasr_mel_filter_ranges": (I, [P, I, P, P]),
@@ -114,6 +115,7 @@ def require_cuda(*ts):
 # ---------------------------------------------------------------------------------------------
 # GEMM
 # ---------------------------------------------------------------------------------------------
+GEMM_PROFILE = None
 EPI_STORE, EPI_RESID, EPI_SWIGLU, EPI_GLU, EPI_SILU, EPI_SWIGLU_BWD, EPI_GLU_BWD, EPI_SILU_BWD, EPI_ATOMIC = range(9)
 
 
@@ -153,6 +155,14 @@ def gemm(M, N, K, A, lda, B, ldb, epilogue, out, ldo, a_mn=0, b_mn=0, out_f32=0,
     a.alpha, a.n_half, a.drop_p, a.seed = alpha, n_half, drop_p, seed
     a.split_k, a.remap_p0, a.remap_p1 = split_k, remap_p0, remap_p1
     fn = lib().tasr_gemm_bf16_debug if debug else lib().tasr_gemm_bf16
+    if GEMM_PROFILE is not None:  # bench.py roofline pass: CUDA events around every tcgen05 GEMM launch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(C.addressof(a), stream_ptr()))
+        e1.record()
+        nb = 2 if epilogue in (EPI_SWIGLU, EPI_GLU) else 1
+        GEMM_PROFILE.append((2.0 * M * N * nb * K, e0, e1, (M, N * nb, K, epilogue, a_mn, b_mn)))
+        return
     check(fn(C.addressof(a), stream_ptr()))
 
 

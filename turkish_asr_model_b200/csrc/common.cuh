@@ -9,8 +9,11 @@
 
 #include "../../include/tasr_kernels.h"
 
+extern unsigned long long g_tasr_launches;  // kernels launched by this library (bench.py reports it)
+
 #define TASR_CHECK_LAUNCH()                                     \
   do {                                                          \
+    ++g_tasr_launches;                                          \
     cudaError_t e__ = cudaGetLastError();                       \
     if (e__ != cudaSuccess) return tasr_set_cuda_error(e__);    \
   } while (0)

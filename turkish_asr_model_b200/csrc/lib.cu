@@ -4,6 +4,9 @@
 #include <string.h>
 
 static thread_local char g_err[512] = "";
+unsigned long long g_tasr_launches = 0;
+
+extern "C" uint64_t tasr_launch_count(void) { return g_tasr_launches; }
 
 int tasr_set_cuda_error(cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "CUDA error %d: %s", (int)e, cudaGetErrorString(e));

@@ -371,8 +371,11 @@ class ConformerEngine:
         dxn = self._ff_backward(pre + "ff1.", dres, sv["ff1"], sv["xn1"].view(M, d), M, drop, seed + 0)
         gn_bwd(dxn, sv["x"], sv["st1"], "norm_ff1.norm", True)
 
-    def backward(self, tape, dlogits):
-        """dlogits (B, T', V) bf16.  Accumulates (+=) every parameter gradient into flat.grads."""
+    def backward(self, tape, dlogits, on_segment_done=None):
+        """dlogits (B, T', V) bf16.  Accumulates (+=) every parameter gradient into flat.grads.
+        on_segment_done(k) is called after the kernels producing gradient segment k have been enqueued
+        (k = 0: classifier, 1..n: blocks n-1..0, n+1: subsampler) so that a data-parallel caller can start
+        that segment's all-reduce while the rest of backward runs."""
         P, S, Gv = self.P, self.S, self.Gv
         d, V, F2 = self.d, self.V, self.F2
         B, T2, M = tape["B"], tape["T2"], tape["M"]
@@ -391,8 +394,12 @@ class ConformerEngine:
         L.colsum_add(dl, Gv("fc.bias"))
         dres = torch.empty(M, d, dtype=torch.float32, device=dev)
         L.gemm(M, d, V, dl, dl.stride(0), S("fc.weight"), d, L.EPI_STORE, dres, d, b_mn=1, out_f32=1)
-        for i in reversed(range(self.n_blocks)):
+        if on_segment_done is not None:
+            on_segment_done(0)
+        for k, i in enumerate(reversed(range(self.n_blocks))):
             self._block_backward(i, dres, tape["blocks"][i], B, T2, tape["key_len"], cs, tape["drop"])
+            if on_segment_done is not None:
+                on_segment_done(1 + k)
         # input_proj + subsampler (model/conformer.py:177-185)
         dx0 = L.cast_bf16(dres)
         y2v = tape["y2"].view(M, F2 * d)
@@ -408,3 +415,5 @@ class ConformerEngine:
         L.gemm(Mpix, 9 * d, d, dz2, d, tape["w2p"], 9 * d, L.EPI_STORE, dcol, 9 * d, b_mn=1)
         L.col2im_conv1_bwd(dcol, tape["feats"], P("subsample.0.weight"), P("subsample.0.bias"),
                            Gv("subsample.0.weight"), Gv("subsample.0.bias"))
+        if on_segment_done is not None:
+            on_segment_done(1 + self.n_blocks)
