@@ -43,6 +43,9 @@ int tasr_version(void);
 int tasr_check_device(void);
 /* number of CUDA kernels this library has launched in this process (monotonic). */
 uint64_t tasr_launch_count(void);
+/* Optional device-resident counter added to every dropout seed at kernel run time (NULL to disable), so that a
+ * captured CUDA graph draws fresh dropout masks on every replay.  Process-global configuration. */
+int tasr_set_dropout_seed_ptr(const uint64_t* dev_ptr);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contractions on tcgen05 / TMEM (bf16 in, fp32 accumulate), operands staged by TMA.

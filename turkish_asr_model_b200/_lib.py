@@ -21,6 +21,7 @@ _SIGNATURES = {
     "tasr_check_device": (I, []),
     "tasr_init": (I, []),
     "tasr_launch_count": (U64, []),
+    "tasr_set_dropout_seed_ptr": (I, [P]),
     "tasr_gemm_bf16": (I, [P, P]),
     "tasr_gemm_bf16_debug": (I, [P, P]),
     "tasr_mel_filter_ranges": (I, [P, I, P, P]),
@@ -101,7 +102,9 @@ def workspace(nbytes, device):
     key = (device.index if device.index is not None else torch.cuda.current_device())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        if torch.cuda.is_current_stream_capturing():
+            raise TasrError("scratch workspace would have to grow during CUDA-graph capture; run one eager step first")
+        buf = torch.empty(max(int(nbytes), 128 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
 
@@ -155,14 +158,9 @@ def gemm(M, N, K, A, lda, B, ldb, epilogue, out, ldo, a_mn=0, b_mn=0, out_f32=0,
     a.alpha, a.n_half, a.drop_p, a.seed = alpha, n_half, drop_p, seed
     a.split_k, a.remap_p0, a.remap_p1 = split_k, remap_p0, remap_p1
     fn = lib().tasr_gemm_bf16_debug if debug else lib().tasr_gemm_bf16
-    if GEMM_PROFILE is not None:  # bench.py roofline pass: CUDA events around every tcgen05 GEMM launch
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        check(fn(C.addressof(a), stream_ptr()))
-        e1.record()
+    if GEMM_PROFILE is not None:  # bench.py roofline pass: remember every tcgen05 GEMM launch of a step
         nb = 2 if epilogue in (EPI_SWIGLU, EPI_GLU) else 1
-        GEMM_PROFILE.append((2.0 * M * N * nb * K, e0, e1, (M, N * nb, K, epilogue, a_mn, b_mn)))
-        return
+        GEMM_PROFILE.append((2.0 * M * N * nb * K, a, (A, B, out, out2, bias, aux), (M, N * nb, K, epilogue, a_mn, b_mn)))
     check(fn(C.addressof(a), stream_ptr()))
 
 
@@ -393,3 +391,11 @@ def argmax_collapse(logits, lengths=None, blank=0):
     check(lib().tasr_argmax_collapse(ptr(logits), int(logits.dtype == torch.bfloat16), ld, B, T, V, ptr(lengths), blank,
                                      ptr(ids), ptr(tokens), ptr(out_len), stream_ptr()))
     return ids, tokens, out_len
+
+
+def gemm_replay(profile):
+    """Re-issue the GEMM launches recorded in GEMM_PROFILE (same argument structs; operands kept alive)."""
+    fn = lib().tasr_gemm_bf16
+    sp = stream_ptr()
+    for _, a, _, _ in profile:
+        check(fn(C.addressof(a), sp))

@@ -27,6 +27,7 @@ struct AttnParams {
   uint32_t drop_thresh;
   float drop_inv_keep;
   unsigned long long seed;
+  const unsigned long long* seed_ptr;
   bf16* ctx;                 // fwd out (B*T, d)
   float* lse2;               // (B, H, T) log2-domain logsumexp
   // backward
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(ATT_THREADS) mqa_fwd_kernel(const __grid_const
     tma_load_3d(sQ, &tm_qkv, &bars[0], h * DH, q0, b);
     tma_load_3d(sQ + 8192, &tm_qkv, &bars[0], h * DH, q0 + 64, b);
   }
+  const unsigned long long dseed = (p.drop_thresh && p.seed_ptr) ? p.seed + *p.seed_ptr : p.seed;
   const float scale2 = p.scale * LOG2E;
   float m_run = -INFINITY, l_run = 0.f;
   float o[DH];
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(ATT_THREADS) mqa_fwd_kernel(const __grid_const
         float e = 0.f;
         if (key < Lk) e = exp2f(__uint_as_float(u[i]) * scale2 - m_new);
         lsum += e;
-        if (p.drop_thresh) e *= dropout_scale(p.seed, drop_index(b, h, p.H, p.T, qrow, key), p.drop_thresh, p.drop_inv_keep);
+        if (p.drop_thresh) e *= dropout_scale(dseed, drop_index(b, h, p.H, p.T, qrow, key), p.drop_thresh, p.drop_inv_keep);
         pv[i] = e;
       }
       store_tile_chunk(sP, tid, c * 32, pv);
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(ATT_THREADS) mqa_bwd_kernel(const __grid_const
     tma_load_3d(sV, &tm_qkv, &bars[0], p.d + DH, k0, b);
     tma_load_3d(sV + 8192, &tm_qkv, &bars[0], p.d + DH, k0 + 64, b);
   }
+  const unsigned long long dseed = (p.drop_thresh && p.seed_ptr) ? p.seed + *p.seed_ptr : p.seed;
   const float scale2 = p.scale * LOG2E;
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);     // Q K^T, dO V^T
   constexpr uint32_t idesc_t = umma_idesc_bf16(128, DH, 1, 1);      // P^T dO, dS^T Q
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(ATT_THREADS) mqa_bwd_kernel(const __grid_const
             pr = exp2f(__uint_as_float(us[i]) * scale2 - lse2);
             float dp = __uint_as_float(ud[i]);
             if (p.drop_thresh) {
-              const float ms = dropout_scale(p.seed, drop_index(b, h, p.H, p.T, qrow, key), p.drop_thresh, p.drop_inv_keep);
+              const float ms = dropout_scale(dseed, drop_index(b, h, p.H, p.T, qrow, key), p.drop_thresh, p.drop_inv_keep);
               dp *= ms;
               ds = pr * (dp - delta) * p.scale;
               pr *= ms;
@@ -462,15 +465,10 @@ void fill_params(AttnParams* p, int B, int T, int H, int d, const int64_t* key_l
   p->B = B; p->T = T; p->H = H; p->d = d;
   p->key_len = reinterpret_cast<const long long*>(key_len);
   p->scale = 0.125f;
-  if (drop_p > 0.f) {
-    double t = (double)drop_p * 4294967296.0;
-    p->drop_thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
-    if (p->drop_thresh == 0) p->drop_thresh = 1;
-    p->drop_inv_keep = 1.f / (1.f - drop_p);
-  } else {
-    p->drop_thresh = 0; p->drop_inv_keep = 1.f;
-  }
+  p->drop_thresh = tasr_drop_thresh16(drop_p);
+  p->drop_inv_keep = tasr_drop_inv_keep(p->drop_thresh);
   p->seed = seed;
+  p->seed_ptr = g_tasr_seed_ptr;
   p->ctx = nullptr; p->lse2 = nullptr; p->delta = nullptr; p->dq_acc = nullptr; p->dqkv = nullptr;
 }
 

@@ -9,7 +9,9 @@
 
 #include "../../include/tasr_kernels.h"
 
-extern unsigned long long g_tasr_launches;  // kernels launched by this library (bench.py reports it)
+extern unsigned long long g_tasr_launches;
+// optional device counter added to every dropout seed (lets a captured CUDA graph draw fresh masks per replay)
+extern const unsigned long long* g_tasr_seed_ptr;  // kernels launched by this library (bench.py reports it)
 
 #define TASR_CHECK_LAUNCH()                                     \
   do {                                                          \
@@ -44,7 +46,7 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 // d/dx silu(x) = s + x*s*(1-s)
 __device__ __forceinline__ float silu_gradf_(float x) {
@@ -60,18 +62,39 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
-// Counter-based dropout mask: keep iff hash(seed, idx) >= p * 2^32. The same function is
-// evaluated in forward and backward, so no mask is ever stored.
-__host__ __device__ __forceinline__ uint32_t tasr_hash32(unsigned long long seed, unsigned long long idx) {
-  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
+// Counter-based dropout mask, evaluated identically in forward and backward (no mask is stored).
+// One 32-bit hash serves TWO neighbouring elements (16-bit lanes): element idx is kept iff
+//   lane16(hash(seed, idx >> 1), idx & 1) >= thresh16,  thresh16 = round(p * 65536).
+__host__ __device__ __forceinline__ uint32_t tasr_hash_pair(unsigned long long seed, unsigned long long pair_idx) {
+  uint32_t x = (uint32_t)pair_idx + (uint32_t)seed;
+  x += (uint32_t)(pair_idx >> 32) * 0x9E3779B1u;
+  x ^= x >> 16; x *= 0x7FEB352Du;
+  x ^= (uint32_t)(seed >> 32);
+  x ^= x >> 15; x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t tasr_drop_thresh16(float p) {
+  if (!(p > 0.f)) return 0u;
+  double t = (double)p * 65536.0 + 0.5;
+  uint32_t v = t >= 65535.0 ? 65535u : (uint32_t)t;
+  return v == 0 ? 1u : v;
+}
+__host__ __device__ __forceinline__ float tasr_drop_inv_keep(uint32_t thresh16) {
+  return thresh16 ? 65536.f / (65536.f - (float)thresh16) : 1.f;
 }
 __device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx,
-                                               uint32_t thresh, float inv_keep) {
-  return tasr_hash32(seed, idx) >= thresh ? inv_keep : 0.f;
+                                               uint32_t thresh16, float inv_keep) {
+  const uint32_t h = tasr_hash_pair(seed, idx >> 1);
+  const uint32_t lane = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+  return lane >= thresh16 ? inv_keep : 0.f;
+}
+// both elements of the pair (idx even, idx + 1) with one hash
+__device__ __forceinline__ void dropout_scale2(unsigned long long seed, unsigned long long idx_even, uint32_t thresh16,
+                                               float inv_keep, float& s0, float& s1) {
+  const uint32_t h = tasr_hash_pair(seed, idx_even >> 1);
+  s0 = (h & 0xFFFFu) >= thresh16 ? inv_keep : 0.f;
+  s1 = (h >> 16) >= thresh16 ? inv_keep : 0.f;
 }
 
 #ifdef __CUDACC__
@@ -190,6 +213,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+
+// ----------------------------------------------------------------------------------------------
+// PTX: TMA stores / reductions (shared -> global), bulk async groups, named barriers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   (uint64_t)m),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // UMMA shared-memory matrix descriptor, 128-byte swizzle (layout type 2), descriptor version 1.
 //   start address / LBO / SBO are encoded in 16-byte units.

@@ -11,16 +11,17 @@ constexpr int NT = 256;
 
 __global__ void __launch_bounds__(NT) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
                                                            long long n, float alpha, uint32_t thresh, float inv_keep,
-                                                           unsigned long long seed) {
+                                                           unsigned long long seed, const unsigned long long* seed_ptr) {
+  if (thresh && seed_ptr) seed += *seed_ptr;
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
     float4 v = *reinterpret_cast<const float4*>(in + i * 4);
     v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
     if (thresh) {
-      v.x *= dropout_scale(seed, i * 4 + 0, thresh, inv_keep);
-      v.y *= dropout_scale(seed, i * 4 + 1, thresh, inv_keep);
-      v.z *= dropout_scale(seed, i * 4 + 2, thresh, inv_keep);
-      v.w *= dropout_scale(seed, i * 4 + 3, thresh, inv_keep);
+      float s0, s1, s2, s3;
+      dropout_scale2(seed, (unsigned long long)i * 4, thresh, inv_keep, s0, s1);
+      dropout_scale2(seed, (unsigned long long)i * 4 + 2, thresh, inv_keep, s2, s3);
+      v.x *= s0; v.y *= s1; v.z *= s2; v.w *= s3;
     }
     uint2 u;
     u.x = pack_bf16x2(v.x, v.y);
@@ -87,17 +88,11 @@ extern "C" int tasr_cast_f32_bf16(const float* in, void* out, int64_t n, float a
                                   tasr_stream_t stream) {
   if (n <= 0) return TASR_OK;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7)) return TASR_ERR_ALIGN;
-  uint32_t thresh = 0;
-  float inv_keep = 1.f;
-  if (drop_p > 0.f) {
-    double t = (double)drop_p * 4294967296.0;
-    thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
-    if (thresh == 0) thresh = 1;
-    inv_keep = 1.f / (1.f - drop_p);
-  }
+  const uint32_t thresh = tasr_drop_thresh16(drop_p);
+  const float inv_keep = tasr_drop_inv_keep(thresh);
   const int grid = (int)imin64((long long)148 * 8, ((n >> 2) + NT) / NT);
   cast_f32_bf16_kernel<<<grid, NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, reinterpret_cast<bf16*>(out), n, alpha,
-                                                                                 thresh, inv_keep, seed);
+                                                                                 thresh, inv_keep, seed, g_tasr_seed_ptr);
   TASR_CHECK_LAUNCH();
   return TASR_OK;
 }

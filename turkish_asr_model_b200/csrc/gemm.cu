@@ -1,10 +1,15 @@
-// bf16 GEMM on tcgen05 / TMEM with TMA-fed shared-memory pipeline and fused epilogues.
-// One CTA = one 128 x BN output tile (cta_group::1), 6 warps:
-//   warp 0     : TMA producer (one elected lane)
-//   warp 1     : TMEM allocator + UMMA issuer (one elected lane)
-//   warps 2..5 : epilogue, one TMEM lane (= tile row) per thread
-// Two CTAs fit per SM (3 stages x 32 KB, 128 TMEM columns each), so one CTA's epilogue overlaps the
-// other's main loop.
+// bf16 GEMM on tcgen05 / TMEM: persistent, warp-specialised, TMA in and TMA out, fused epilogues.
+//
+//   grid  = min(#tiles, #SMs) persistent CTAs, static round-robin tile schedule (n fastest, so CTAs that
+//           run together share A rows in L2)
+//   warp 0     : TMA producer       (smem ring of STAGES x {A 128x64, B BNx64} bf16, 128 B swizzle)
+//   warp 1     : TMEM allocator + UMMA issuer (cta_group::1, 128 x BN x 16 per instruction)
+//   warps 2..5 : epilogue: TMEM -> registers -> fused math -> swizzled smem staging -> TMA store
+//   TMEM holds TWO accumulators (2 x BN fp32 columns): the epilogue of tile i overlaps the main loop of
+//   tile i+1, which matters because most GEMMs of this model have K = 256 (4 k-blocks per tile).
+//
+// Replaces (reference): every nn.Linear / 1x1 Conv1d / Conv2d-as-GEMM and their autograd backward, see
+// include/tasr_kernels.h.
 #include "common.cuh"
 #include <stdio.h>
 #include <string.h>
@@ -14,7 +19,10 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;       // producer warp + MMA warp + 8 epilogue warps
+constexpr int EPI_THREADS = 256;
+constexpr int EPI_GROUP_THREADS = 128;  // one epilogue group = 4 warps = the 4 TMEM lane quarters
+constexpr int STAGE_BYTES = 16384;  // 128 rows x 128 B
 
 struct GemmDev {
   int M, N, K;
@@ -32,32 +40,13 @@ struct GemmDev {
   uint32_t drop_thresh;
   float drop_inv_keep;
   unsigned long long seed;
+  const unsigned long long* seed_ptr;
   int kb_per_split;
+  int splits;
   int remap_p0, remap_p1;
+  int tiles_m, tiles_n;
 };
 
-// ------------------------------------------------------------------------------------------------
-// Epilogue on one row chunk of 32 columns (shared by the tcgen05 kernel and the debug kernel).
-//   lo[]: accumulator columns [col0, col0+32);   hi[]: dual-B modes only, the paired half.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_bf16_chunk(bf16* dst, const float* v, int nvalid) {
-  if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-      u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      d4[i] = u;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < nvalid) dst[i] = __float2bfloat16(v[i]);
-  }
-}
 __device__ __forceinline__ void load_bf16_chunk(const bf16* src, float* v, int nvalid) {
   if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
@@ -75,17 +64,6 @@ __device__ __forceinline__ void load_bf16_chunk(const bf16* src, float* v, int n
     for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? __bfloat162float(src[i]) : 0.f;
   }
 }
-__device__ __forceinline__ void store_f32_chunk(float* dst, const float* v, int nvalid) {
-  if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-    float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < nvalid) dst[i] = v[i];
-  }
-}
 __device__ __forceinline__ void load_f32_chunk(const float* src, float* v, int nvalid) {
   if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -101,146 +79,169 @@ __device__ __forceinline__ void load_f32_chunk(const float* src, float* v, int n
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
-__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, int row, int col0, float* lo, float* hi) {
-  const int nvalid = min(32, p.N - col0);
-  if (nvalid <= 0) return;
+// ------------------------------------------------------------------------------------------------
+// Fused epilogue math on one row chunk of 32 columns [col0, col0+32) of output row `row`.
+//   in : lo = accumulator;  hi = paired accumulator (dual-B modes)
+//   out: lo = primary output, hi = second output, t3 = third output (see table below)
+//     STORE / RESID / SILU_BWD / ATOMIC : lo -> out
+//     SWIGLU / GLU                      : t3 -> out (h|u), lo -> out2[:, col] (g|a), hi -> out2[:, n_half+col]
+//     SILU                              : t3 -> out (silu(z)), lo -> out2 (z)
+//     SWIGLU_BWD / GLU_BWD              : lo -> out[:, col], hi -> out[:, n_half+col]
+// Rows >= M or columns >= N produce don't-care values (clipped by the TMA store / masked by the caller).
+// The mode is a template parameter: only that mode's code is generated (the step is epilogue-bound for
+// the K = 256 GEMMs, and one 32-column chunk of a generic switch was ~15k SASS instructions).
+// ------------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col0, float* lo, float* hi, float* t3) {
+  const int nvalid = (row < p.M) ? max(0, min(32, p.N - col0)) : 0;
   const long long r = row;
-  switch (p.epi) {
-    case TASR_EPI_STORE: {
+  const unsigned long long seed = (p.drop_thresh && p.seed_ptr) ? p.seed + *p.seed_ptr : p.seed;
+  const unsigned long long idx0 = (unsigned long long)(r * p.N + col0);  // even: N is even when dropout is on
+  if (EPI == TASR_EPI_STORE) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float b = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
-        lo[i] = p.alpha * (lo[i] + b);
+    for (int i = 0; i < 32; ++i) {
+      const float b = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
+      lo[i] = p.alpha * (lo[i] + b);
+    }
+  } else if (EPI == TASR_EPI_RESID) {
+    load_f32_chunk(reinterpret_cast<const float*>(p.aux) + r * p.ldaux + col0, t3, nvalid);
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float b0 = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
+      const float b1 = (p.bias != nullptr && i + 1 < nvalid) ? p.bias[col0 + i + 1] : 0.f;
+      float v0 = lo[i] + b0, v1 = lo[i + 1] + b1;
+      if (p.drop_thresh) {
+        float s0, s1;
+        dropout_scale2(seed, idx0 + i, p.drop_thresh, p.drop_inv_keep, s0, s1);
+        v0 *= s0; v1 *= s1;
       }
-      if (p.out_f32)
-        store_f32_chunk(reinterpret_cast<float*>(p.out) + r * p.ldo + col0, lo, nvalid);
-      else
-        store_bf16_chunk(reinterpret_cast<bf16*>(p.out) + r * p.ldo + col0, lo, nvalid);
-    } break;
-    case TASR_EPI_RESID: {
-      float res[32];
-      load_f32_chunk(reinterpret_cast<const float*>(p.aux) + r * p.ldaux + col0, res, nvalid);
+      lo[i] = t3[i] + p.alpha * v0;
+      lo[i + 1] = t3[i + 1] + p.alpha * v1;
+    }
+  } else if (EPI == TASR_EPI_SWIGLU || EPI == TASR_EPI_GLU) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float b = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
-        float v = lo[i] + b;
-        if (p.drop_thresh) v *= dropout_scale(p.seed, (unsigned long long)(r * p.N + col0 + i), p.drop_thresh, p.drop_inv_keep);
-        lo[i] = res[i] + p.alpha * v;
+    for (int i = 0; i < 32; i += 2) {
+      float s0 = 1.f, s1 = 1.f;
+      if (p.drop_thresh) dropout_scale2(seed, idx0 + i, p.drop_thresh, p.drop_inv_keep, s0, s1);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = i + j;
+        const float b0 = (p.bias != nullptr && k < nvalid) ? p.bias[col0 + k] : 0.f;
+        const float b1 = (p.bias != nullptr && k < nvalid) ? p.bias[p.n_half + col0 + k] : 0.f;
+        lo[k] = bf16_round(lo[k] + b0);
+        hi[k] = bf16_round(hi[k] + b1);
+        const float v = (EPI == TASR_EPI_SWIGLU) ? siluf_(lo[k]) * hi[k] : lo[k] * sigmoidf_(hi[k]);
+        t3[k] = v * (j == 0 ? s0 : s1);
       }
-      store_f32_chunk(reinterpret_cast<float*>(p.out) + r * p.ldo + col0, lo, nvalid);
-    } break;
-    case TASR_EPI_SWIGLU:
-    case TASR_EPI_GLU: {
+    }
+  } else if (EPI == TASR_EPI_SILU) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float b0 = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
-        float b1 = (p.bias != nullptr && i < nvalid) ? p.bias[p.n_half + col0 + i] : 0.f;
-        lo[i] = bf16_round(lo[i] + b0);
-        hi[i] = bf16_round(hi[i] + b1);
-      }
-      bf16* o2 = reinterpret_cast<bf16*>(p.out2) + r * p.ldo2;
-      store_bf16_chunk(o2 + col0, lo, nvalid);
-      store_bf16_chunk(o2 + p.n_half + col0, hi, nvalid);
+    for (int i = 0; i < 32; ++i) {
+      const float b = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
+      lo[i] = bf16_round(lo[i] + b);
+      t3[i] = siluf_(lo[i]);
+    }
+  } else if (EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) {
+    const bf16* ax = reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux;
+    load_bf16_chunk(ax + col0, hi, nvalid);             // g | a
+    load_bf16_chunk(ax + p.n_half + col0, t3, nvalid);  // v | b
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float v = (p.epi == TASR_EPI_SWIGLU) ? siluf_(lo[i]) * hi[i] : lo[i] * sigmoidf_(hi[i]);
-        if (p.drop_thresh) v *= dropout_scale(p.seed, (unsigned long long)(r * p.N + col0 + i), p.drop_thresh, p.drop_inv_keep);
-        lo[i] = v;
-      }
-      store_bf16_chunk(reinterpret_cast<bf16*>(p.out) + r * p.ldo + col0, lo, nvalid);
-    } break;
-    case TASR_EPI_SILU: {
+    for (int i = 0; i < 32; i += 2) {
+      float s0 = 1.f, s1 = 1.f;
+      if (p.drop_thresh) dropout_scale2(seed, idx0 + i, p.drop_thresh, p.drop_inv_keep, s0, s1);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float b = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
-        lo[i] = bf16_round(lo[i] + b);
-      }
-      if (p.out2 != nullptr) store_bf16_chunk(reinterpret_cast<bf16*>(p.out2) + r * p.ldo2 + col0, lo, nvalid);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) lo[i] = siluf_(lo[i]);
-      store_bf16_chunk(reinterpret_cast<bf16*>(p.out) + r * p.ldo + col0, lo, nvalid);
-    } break;
-    case TASR_EPI_SWIGLU_BWD:
-    case TASR_EPI_GLU_BWD: {
-      float g[32], v[32];
-      const bf16* ax = reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux;
-      load_bf16_chunk(ax + col0, g, nvalid);
-      load_bf16_chunk(ax + p.n_half + col0, v, nvalid);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float d = lo[i];
-        if (p.drop_thresh) d *= dropout_scale(p.seed, (unsigned long long)(r * p.N + col0 + i), p.drop_thresh, p.drop_inv_keep);
-        if (p.epi == TASR_EPI_SWIGLU_BWD) {
-          lo[i] = d * v[i] * silu_gradf_(g[i]);  // d/dg
-          hi[i] = d * siluf_(g[i]);              // d/dv
+      for (int j = 0; j < 2; ++j) {
+        const int k = i + j;
+        const float d = lo[k] * (j == 0 ? s0 : s1);
+        const float g = hi[k], v = t3[k];
+        if (EPI == TASR_EPI_SWIGLU_BWD) {
+          const float sg = sigmoidf_(g);
+          lo[k] = d * v * sg * (1.f + g * (1.f - sg));  // d/dg
+          hi[k] = d * g * sg;                            // d/dv
         } else {
-          float s = sigmoidf_(v[i]);
-          lo[i] = d * s;                         // d/da
-          hi[i] = d * g[i] * s * (1.f - s);      // d/db
+          const float sv = sigmoidf_(v);
+          lo[k] = d * sv;                                // d/da
+          hi[k] = d * g * sv * (1.f - sv);               // d/db
         }
       }
-      bf16* o = reinterpret_cast<bf16*>(p.out) + r * p.ldo;
-      store_bf16_chunk(o + col0, lo, nvalid);
-      store_bf16_chunk(o + p.n_half + col0, hi, nvalid);
-    } break;
-    case TASR_EPI_SILU_BWD: {
-      float z[32];
-      load_bf16_chunk(reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux + col0, z, nvalid);
+    }
+  } else if (EPI == TASR_EPI_SILU_BWD) {
+    load_bf16_chunk(reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux + col0, t3, nvalid);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) lo[i] = lo[i] * silu_gradf_(z[i]);
-      store_bf16_chunk(reinterpret_cast<bf16*>(p.out) + r * p.ldo + col0, lo, nvalid);
-    } break;
-    case TASR_EPI_ATOMIC: {
-      float* o = reinterpret_cast<float*>(p.out) + r * p.ldo;
+    for (int i = 0; i < 32; ++i) lo[i] = lo[i] * silu_gradf_(t3[i]);
+  } else if (EPI == TASR_EPI_ATOMIC) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i >= nvalid) break;
-        int c = col0 + i;
-        if (p.remap_p0 > 0) c = (c % p.remap_p0) * p.remap_p1 + c / p.remap_p0;
-        atomicAdd(o + c, p.alpha * lo[i]);
-      }
-    } break;
-    default: break;
+    for (int i = 0; i < 32; ++i) lo[i] *= p.alpha;
   }
 }
 
+// staging writes: row r of a [128 rows x 128 B] buffer in the TMA 128-byte swizzle
+__device__ __forceinline__ void stage_bf16_half(uint8_t* buf, int r, int half, const float* v) {
+  uint8_t* base = buf + r * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(base + (((half * 4 + i) ^ (r & 7)) << 4)) = u;
+  }
+}
+__device__ __forceinline__ void stage_f32(uint8_t* buf, int r, const float* v) {
+  uint8_t* base = buf + r * 128;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(base + ((i ^ (r & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
 // ------------------------------------------------------------------------------------------------
-// tcgen05 kernel
+// the kernel
+//   EPI    epilogue mode (compile time)          BN     accumulator width (dual-B modes: BN/2 output cols)
+//   STAGES smem pipeline depth                   RINGG  staging buffers per epilogue group
+//   two epilogue groups of 4 warps each take alternate 64-column groups of a tile
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool DUAL>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+template <int EPI, int BN, int STAGES, int RINGG, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmDev p) {
+  constexpr bool DUAL = (EPI == TASR_EPI_SWIGLU || EPI == TASR_EPI_GLU);
   constexpr int A_BYTES = BM * BK * 2;  // 16 KB
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr uint32_t TMEM_COLS = BN;  // power of two >= 32
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulators
+  constexpr int TILE_N = DUAL ? BN / 2 : BN;
+  constexpr int NBUF = DUAL ? 3 : ((EPI == TASR_EPI_SILU || EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) ? 2 : 1);
+  static_assert(RINGG >= NBUF, "staging ring too small");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint8_t* sC = sB + STAGES * B_BYTES;  // 2 groups x RINGG staging buffers
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sC + 2 * RINGG * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
-  const int m0 = m_tile * BM;
-  const int n0 = DUAL ? n_tile * (BN / 2) : n_tile * BN;
   const int num_kb_total = (p.K + BK - 1) / BK;
-  const int kb_begin = split * p.kb_per_split;
-  const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
-  const int num_kb = kb_end - kb_begin;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.splits;
 
-  if (warp == 0 && lane == 0) {
+  if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    tma_prefetch_desc(&tmO2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], EPI_THREADS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -249,16 +250,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (num_kb > 0) {
-    if (warp == 0) {
-      // ===================== TMA producer =====================
-      if (elect_one()) {
-        for (int i = 0; i < num_kb; ++i) {
-          const int s = i % STAGES;
-          const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.tiles_n;
+        const int m_tile = (tile / p.tiles_n) % p.tiles_m;
+        const int split = tile / (p.tiles_n * p.tiles_m);
+        const int m0 = m_tile * BM, n0 = n_tile * TILE_N;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-          const int k0 = (kb_begin + i) * BK;
+          const int k0 = kb * BK;
           uint8_t* a_dst = sA + s * A_BYTES;
           uint8_t* b_dst = sB + s * B_BYTES;
 #pragma unroll
@@ -268,21 +276,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) {
-            int nrow = DUAL ? (j < BN / 128 ? n0 + 64 * j : p.n_half + n0 + 64 * (j - BN / 128)) : n0 + 64 * j;
+            const int nrow = DUAL ? (j < BN / 128 ? n0 + 64 * j : p.n_half + n0 + 64 * (j - BN / 128)) : n0 + 64 * j;
             if (B_MN) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], nrow, k0);
             else      tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], k0, nrow);
           }
         }
       }
-    } else if (warp == 1) {
-      // ===================== UMMA issuer =====================
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int split = tile / (p.tiles_n * p.tiles_m);
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+        const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+        mbar_wait(&tempty_bar[acc], aph ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        if (elect_one()) {
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
           const uint32_t a_base = smem_u32(sA + s * A_BYTES);
           const uint32_t b_base = smem_u32(sB + s * B_BYTES);
 #pragma unroll
@@ -293,34 +311,136 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         : umma_desc_sw128(a_base + k * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? umma_desc_sw128(b_base + k * 2048, 8192, 1024)
                                         : umma_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_bf16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);                    // frees the smem stage when the MMAs retire
-          if (i == num_kb - 1) umma_commit(accum_bar);   // accumulator complete
+          umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
         }
-        __syncwarp();
-      }
-    } else {
-      // ===================== epilogue =====================
-      const int q = warp & 3;  // TMEM lane quarter this warp may access
-      const int row = m0 + q * 32 + lane;
-      mbar_wait(accum_bar, 0);
-      tc_fence_after();
-      constexpr int NCH = DUAL ? BN / 64 : BN / 32;
-#pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        uint32_t lo_u[32], hi_u[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-        tmem_ld32(taddr, lo_u);
-        if (DUAL) tmem_ld32(taddr + BN / 2, hi_u);
-        tmem_ld_wait();
-        if (row < p.M) {
-          float* lo = reinterpret_cast<float*>(lo_u);
-          float* hi = reinterpret_cast<float*>(hi_u);
-          epilogue_chunk(p, row, n0 + c * 32, lo, hi);
-        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
       }
     }
+  } else {
+    // ===================== epilogue: 2 groups x 4 warps =====================
+    const int ew = warp - 2;        // 0..7
+    const int grp = ew >> 2;        // epilogue group
+    const int q = warp & 3;         // TMEM lane quarter this warp may access
+    const int rloc = q * 32 + lane;
+    const bool leader = (q == ((2 + grp * 4) & 3)) && lane == 0;  // first warp of the group
+    const int bar_id = 1 + grp;
+    uint8_t* ring_base = sC + grp * RINGG * STAGE_BYTES;
+    constexpr bool F32_MODE = (EPI == TASR_EPI_RESID || EPI == TASR_EPI_ATOMIC);
+    const bool f32_out = F32_MODE || (EPI == TASR_EPI_STORE && p.out_f32);
+    const bool direct_atomic = (EPI == TASR_EPI_ATOMIC) && (p.remap_p0 > 0);
+    uint32_t tcount = 0, ring = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int n_tile = tile % p.tiles_n;
+      const int m_tile = (tile / p.tiles_n) % p.tiles_m;
+      const int m0 = m_tile * BM, n0 = n_tile * TILE_N;
+      const int row = m0 + rloc;
+      const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+      mbar_wait(&tfull_bar[acc], aph);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int g = grp; g < TILE_N / 64; g += 2) {  // this group's 64-column groups
+        if (n0 + g * 64 >= p.N) break;               // fully out of range (uniform across the group)
+        if (f32_out) {
+          if (EPI == TASR_EPI_STORE || F32_MODE) {
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+              const int col0 = n0 + g * 64 + h * 32;
+              uint32_t lo_u[32];
+              tmem_ld32(tbase + g * 64 + h * 32, lo_u);
+              tmem_ld_wait();
+              float* lo = reinterpret_cast<float*>(lo_u);
+              float t3[32];
+              epilogue_math<EPI>(p, row, col0, lo, lo, t3);
+              if (direct_atomic) {
+                if (row < p.M) {
+                  float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo;
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    int c = col0 + i;
+                    if (c < p.N) {
+                      c = (c % p.remap_p0) * p.remap_p1 + c / p.remap_p0;
+                      atomicAdd(o + c, lo[i]);
+                    }
+                  }
+                }
+                continue;
+              }
+              if (leader) bulk_wait_read<RINGG - 1>();
+              named_bar_sync(bar_id, EPI_GROUP_THREADS);
+              uint8_t* buf = ring_base + (ring % RINGG) * STAGE_BYTES;
+              stage_f32(buf, rloc, lo);
+              fence_proxy_async_smem();
+              named_bar_sync(bar_id, EPI_GROUP_THREADS);
+              if (leader) {
+                if (EPI == TASR_EPI_ATOMIC) tma_reduce_add_2d(&tmO, buf, col0, m0);
+                else tma_store_2d(&tmO, buf, col0, m0);
+                bulk_commit();
+              }
+              ++ring;
+            }
+          }
+        } else if (!F32_MODE) {
+          // bf16 outputs: NBUF 64-column staging buffers per group
+          if (leader) bulk_wait_read<RINGG - NBUF>();
+          named_bar_sync(bar_id, EPI_GROUP_THREADS);
+          uint8_t* buf0 = ring_base + (ring % RINGG) * STAGE_BYTES;
+          uint8_t* buf1 = ring_base + ((ring + 1) % RINGG) * STAGE_BYTES;
+          uint8_t* buf2 = ring_base + ((ring + 2) % RINGG) * STAGE_BYTES;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            const int col0 = n0 + g * 64 + h * 32;
+            uint32_t lo_u[32], hi_u[32];
+            tmem_ld32(tbase + g * 64 + h * 32, lo_u);
+            if (DUAL) tmem_ld32(tbase + BN / 2 + g * 64 + h * 32, hi_u);
+            tmem_ld_wait();
+            float* lo = reinterpret_cast<float*>(lo_u);
+            float* hi = reinterpret_cast<float*>(hi_u);
+            float t3[32];
+            epilogue_math<EPI>(p, row, col0, lo, hi, t3);
+            if (DUAL) {
+              stage_bf16_half(buf0, rloc, h, t3);
+              stage_bf16_half(buf1, rloc, h, lo);
+              stage_bf16_half(buf2, rloc, h, hi);
+            } else if (EPI == TASR_EPI_SILU) {
+              stage_bf16_half(buf0, rloc, h, t3);
+              stage_bf16_half(buf1, rloc, h, lo);
+            } else if (EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) {
+              stage_bf16_half(buf0, rloc, h, lo);
+              stage_bf16_half(buf1, rloc, h, hi);
+            } else {
+              stage_bf16_half(buf0, rloc, h, lo);
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, EPI_GROUP_THREADS);
+          if (leader) {
+            const int c = n0 + g * 64;
+            if (DUAL) {
+              tma_store_2d(&tmO, buf0, c, m0); bulk_commit();
+              tma_store_2d(&tmO2, buf1, c, m0); bulk_commit();
+              tma_store_2d(&tmO2, buf2, p.n_half + c, m0); bulk_commit();
+            } else if (EPI == TASR_EPI_SILU) {
+              tma_store_2d(&tmO, buf0, c, m0); bulk_commit();
+              if (p.out2 != nullptr) tma_store_2d(&tmO2, buf1, c, m0);
+              bulk_commit();
+            } else if (EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) {
+              tma_store_2d(&tmO, buf0, c, m0); bulk_commit();
+              tma_store_2d(&tmO, buf1, p.n_half + c, m0); bulk_commit();
+            } else {
+              tma_store_2d(&tmO, buf0, c, m0); bulk_commit();
+            }
+          }
+          ring += NBUF;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);  // all 256 epilogue threads: this accumulator may be overwritten
+    }
+    if (leader) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -328,8 +448,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Debug CUDA-core kernel (tests / triage only): one thread per (row, 32-col chunk)
+// Debug CUDA-core kernel (tests / triage only): one thread per (row, 32-col chunk), direct stores
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dbg_store(void* base, long long ld, int is_f32, long long r, int c, float v) {
+  if (is_f32) reinterpret_cast<float*>(base)[r * ld + c] = v;
+  else reinterpret_cast<bf16*>(base)[r * ld + c] = __float2bfloat16(v);
+}
 __global__ void gemm_debug_kernel(const bf16* A, long long lda, int a_mn, const bf16* B, long long ldb, int b_mn,
                                   GemmDev p, int dual) {
   const int chunks = (p.N + 31) / 32;
@@ -337,7 +461,7 @@ __global__ void gemm_debug_kernel(const bf16* A, long long lda, int a_mn, const 
   if (gid >= (long long)p.M * chunks) return;
   const int row = (int)(gid / chunks);
   const int col0 = (int)(gid % chunks) * 32;
-  float lo[32], hi[32];
+  float lo[32], hi[32], t3[32];
   for (int i = 0; i < 32; ++i) {
     float s0 = 0.f, s1 = 0.f;
     const int n = col0 + i;
@@ -355,7 +479,47 @@ __global__ void gemm_debug_kernel(const bf16* A, long long lda, int a_mn, const 
     lo[i] = s0;
     hi[i] = s1;
   }
-  epilogue_chunk(p, row, col0, lo, hi);
+  switch (p.epi) {
+    case TASR_EPI_STORE: epilogue_math<TASR_EPI_STORE>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_RESID: epilogue_math<TASR_EPI_RESID>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_SWIGLU: epilogue_math<TASR_EPI_SWIGLU>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_GLU: epilogue_math<TASR_EPI_GLU>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_SILU: epilogue_math<TASR_EPI_SILU>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_SWIGLU_BWD: epilogue_math<TASR_EPI_SWIGLU_BWD>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_GLU_BWD: epilogue_math<TASR_EPI_GLU_BWD>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_SILU_BWD: epilogue_math<TASR_EPI_SILU_BWD>(p, row, col0, lo, hi, t3); break;
+    default: epilogue_math<TASR_EPI_ATOMIC>(p, row, col0, lo, hi, t3); break;
+  }
+  const bool f32_out = (p.epi == TASR_EPI_RESID) || (p.epi == TASR_EPI_ATOMIC) || (p.epi == TASR_EPI_STORE && p.out_f32);
+  for (int i = 0; i < 32; ++i) {
+    const int c = col0 + i;
+    if (c >= p.N) break;
+    switch (p.epi) {
+      case TASR_EPI_SWIGLU:
+      case TASR_EPI_GLU:
+        dbg_store(p.out, p.ldo, 0, row, c, t3[i]);
+        dbg_store(p.out2, p.ldo2, 0, row, c, lo[i]);
+        dbg_store(p.out2, p.ldo2, 0, row, p.n_half + c, hi[i]);
+        break;
+      case TASR_EPI_SILU:
+        dbg_store(p.out, p.ldo, 0, row, c, t3[i]);
+        if (p.out2) dbg_store(p.out2, p.ldo2, 0, row, c, lo[i]);
+        break;
+      case TASR_EPI_SWIGLU_BWD:
+      case TASR_EPI_GLU_BWD:
+        dbg_store(p.out, p.ldo, 0, row, c, lo[i]);
+        dbg_store(p.out, p.ldo, 0, row, p.n_half + c, hi[i]);
+        break;
+      case TASR_EPI_ATOMIC: {
+        int cc = c;
+        if (p.remap_p0 > 0) cc = (c % p.remap_p0) * p.remap_p1 + c / p.remap_p0;
+        atomicAdd(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + cc, lo[i]);
+      } break;
+      default:
+        dbg_store(p.out, p.ldo, f32_out ? 1 : 0, row, c, lo[i]);
+        break;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -366,6 +530,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled g_encode = nullptr;
 std::once_flag g_encode_once;
+int g_num_sms = 0;
 
 void init_encode() {
   void* fn = nullptr;
@@ -373,24 +538,32 @@ void init_encode() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
       qres == cudaDriverEntryPointSuccess)
     g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (g_num_sms <= 0) g_num_sms = 148;
+}
+
+int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, uint64_t inner, uint64_t outer,
+                 uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  std::call_once(g_encode_once, init_encode);
+  if (!g_encode) return TASR_ERR_CUDA;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * esize};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? TASR_OK : TASR_ERR_CUDA;
 }
 
 }  // namespace
 
 // 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows of pitch ld elements,
-// box = 64 (inner) x box_outer, 128 B swizzle, zero fill out of bounds.
+// 128 B swizzle, zero fill out of bounds.
 int tasr_make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                            uint32_t box_inner, uint32_t box_outer) {
-  std::call_once(g_encode_once, init_encode);
-  if (!g_encode) return TASR_ERR_CUDA;
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? TASR_OK : TASR_ERR_CUDA;
+  return make_tmap_2d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, inner, outer, ld_elems, box_inner, box_outer);
 }
 
 namespace {
@@ -407,29 +580,29 @@ int fill_dev(const tasr_gemm_args* a, GemmDev* p, bool* dual) {
   p->out = a->out; p->ldo = a->ldo; p->out2 = a->out2; p->ldo2 = a->ldo2;
   p->bias = a->bias; p->aux = a->aux; p->ldaux = a->ldaux;
   p->alpha = a->alpha; p->n_half = a->n_half;
-  if (a->drop_p > 0.f) {
-    double t = (double)a->drop_p * 4294967296.0;
-    p->drop_thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
-    if (p->drop_thresh == 0) p->drop_thresh = 1;
-    p->drop_inv_keep = 1.f / (1.f - a->drop_p);
-  } else {
-    p->drop_thresh = 0; p->drop_inv_keep = 1.f;
-  }
+  p->drop_thresh = tasr_drop_thresh16(a->drop_p);
+  p->drop_inv_keep = tasr_drop_inv_keep(p->drop_thresh);
+  if (p->drop_thresh && (a->N & 1)) return TASR_ERR_SHAPE;  // the pair-hash dropout mask needs an even row length
   p->seed = a->seed;
+  p->seed_ptr = g_tasr_seed_ptr;
   p->remap_p0 = a->remap_p0; p->remap_p1 = a->remap_p1;
   const int num_kb = (a->K + BK - 1) / BK;
   int splits = (a->epilogue == TASR_EPI_ATOMIC && a->split_k > 1) ? a->split_k : 1;
   if (splits > num_kb) splits = num_kb;
   p->kb_per_split = (num_kb + splits - 1) / splits;
+  p->splits = (num_kb + p->kb_per_split - 1) / p->kb_per_split;
+  p->tiles_m = p->tiles_n = 1;
   return TASR_OK;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool DUAL>
-int launch_tc(const tasr_gemm_args* a, const GemmDev& p, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
-  CUtensorMap tmA, tmB;
+template <int EPI, int BN, int STAGES, int RINGG, bool A_MN, bool B_MN>
+int launch_tc(const tasr_gemm_args* a, GemmDev& p, cudaStream_t st) {
+  constexpr bool DUAL = (EPI == TASR_EPI_SWIGLU || EPI == TASR_EPI_GLU);
+  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 2 * RINGG * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static_assert(SMEM <= 232448, "shared memory budget");
+  constexpr int TILE_N = DUAL ? BN / 2 : BN;
+  CUtensorMap tmA, tmB, tmO, tmO2;
   int rc;
-  // A: K-major -> dims {K, M}; MN-major -> dims {M, K}
   if (A_MN) rc = tasr_make_tmap_2d_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, 64);
   else      rc = tasr_make_tmap_2d_bf16(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, 64, 64);
   if (rc) return rc;
@@ -437,20 +610,55 @@ int launch_tc(const tasr_gemm_args* a, const GemmDev& p, cudaStream_t st) {
   if (B_MN) rc = tasr_make_tmap_2d_bf16(&tmB, a->B, nrows, (uint64_t)a->K, (uint64_t)a->ldb, 64, 64);
   else      rc = tasr_make_tmap_2d_bf16(&tmB, a->B, (uint64_t)a->K, nrows, (uint64_t)a->ldb, 64, 64);
   if (rc) return rc;
-  auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, DUAL>;
+  // output maps (TMA store clips rows >= M and columns >= the map width)
+  const bool f32_out = EPI == TASR_EPI_RESID || EPI == TASR_EPI_ATOMIC || (EPI == TASR_EPI_STORE && a->out_f32);
+  const bool direct_atomic = EPI == TASR_EPI_ATOMIC && a->remap_p0 > 0;
+  const uint64_t out_cols = (EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) ? (uint64_t)2 * a->n_half : (uint64_t)a->N;
+  if (!direct_atomic) {
+    if (f32_out) {
+      if ((reinterpret_cast<uintptr_t>(a->out) & 15) || (a->ldo & 3)) return TASR_ERR_ALIGN;
+      rc = make_tmap_2d(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, out_cols, (uint64_t)a->M, (uint64_t)a->ldo, 32, 128);
+    } else {
+      if ((reinterpret_cast<uintptr_t>(a->out) & 15) || (a->ldo & 7)) return TASR_ERR_ALIGN;
+      rc = make_tmap_2d(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->out, out_cols, (uint64_t)a->M, (uint64_t)a->ldo, 64, 128);
+    }
+    if (rc) return rc;
+  } else {
+    tmO = tmA;
+  }
+  if (a->out2 != nullptr && (DUAL || EPI == TASR_EPI_SILU)) {
+    if ((reinterpret_cast<uintptr_t>(a->out2) & 15) || (a->ldo2 & 7)) return TASR_ERR_ALIGN;
+    const uint64_t cols2 = DUAL ? (uint64_t)2 * a->n_half : (uint64_t)a->N;
+    rc = make_tmap_2d(&tmO2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->out2, cols2, (uint64_t)a->M, (uint64_t)a->ldo2, 64, 128);
+    if (rc) return rc;
+  } else {
+    if (DUAL) return TASR_ERR_SHAPE;  // dual-B modes need out2
+    tmO2 = tmO;
+  }
+  auto kern = gemm_tc_kernel<EPI, BN, STAGES, RINGG, A_MN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return tasr_set_cuda_error(e);
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (err != cudaSuccess) return tasr_set_cuda_error(err);
     attr_done = true;
   }
-  const int tile_n = DUAL ? BN / 2 : BN;
-  const int num_kb = (a->K + BK - 1) / BK;
-  const int splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
-  dim3 grid(cdiv(a->N, tile_n), cdiv(a->M, BM), splits);
-  kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, p);
+  p.tiles_m = cdiv(a->M, BM);
+  p.tiles_n = cdiv(a->N, TILE_N);
+  const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
+  const int grid = (int)(total < g_num_sms ? total : g_num_sms);
+  kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, tmO, tmO2, p);
   TASR_CHECK_LAUNCH();
   return TASR_OK;
+}
+
+// tile width: wide tiles when they divide N (or N is large); they halve the shared-memory traffic per flop
+inline bool use_wide(int N) { return (N % 256 == 0) || (N > 512 && (N % 256) > 128); }
+
+template <int EPI, bool A_MN, bool B_MN>
+int launch_single(const tasr_gemm_args* a, GemmDev& p, cudaStream_t st) {
+  constexpr int R = (EPI == TASR_EPI_SILU || EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) ? 2 : 2;
+  if (use_wide(a->N)) return launch_tc<EPI, 256, 3, R, A_MN, B_MN>(a, p, st);
+  return launch_tc<EPI, 128, 4, R, A_MN, B_MN>(a, p, st);
 }
 
 }  // namespace
@@ -461,15 +669,43 @@ extern "C" int tasr_gemm_bf16(const tasr_gemm_args* a, tasr_stream_t stream) {
   int rc = fill_dev(a, &p, &dual);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dual) {
-    if (a->a_mn_major || a->b_mn_major) return TASR_ERR_SHAPE;
-    if (a->n_half % 64) return TASR_ERR_SHAPE;
-    return launch_tc<128, 3, false, false, true>(a, p, st);
+  std::call_once(g_encode_once, init_encode);
+  const int am = a->a_mn_major ? 1 : 0, bm = a->b_mn_major ? 1 : 0;
+  switch (a->epilogue) {
+    case TASR_EPI_STORE:
+      if (!am && !bm) return launch_single<TASR_EPI_STORE, false, false>(a, p, st);
+      if (!am && bm) return launch_single<TASR_EPI_STORE, false, true>(a, p, st);
+      if (am && bm) return launch_single<TASR_EPI_STORE, true, true>(a, p, st);
+      return launch_tc<TASR_EPI_STORE, 128, 4, 2, true, false>(a, p, st);
+    case TASR_EPI_RESID:
+      if (!am && !bm) return launch_single<TASR_EPI_RESID, false, false>(a, p, st);
+      break;
+    case TASR_EPI_SWIGLU:
+      if (am || bm || (a->n_half % 64)) break;
+      if (a->n_half % 128 == 0) return launch_tc<TASR_EPI_SWIGLU, 256, 2, 3, false, false>(a, p, st);
+      return launch_tc<TASR_EPI_SWIGLU, 128, 3, 3, false, false>(a, p, st);
+    case TASR_EPI_GLU:
+      if (am || bm || (a->n_half % 64)) break;
+      if (a->n_half % 128 == 0) return launch_tc<TASR_EPI_GLU, 256, 2, 3, false, false>(a, p, st);
+      return launch_tc<TASR_EPI_GLU, 128, 3, 3, false, false>(a, p, st);
+    case TASR_EPI_SILU:
+      if (!am && !bm) return launch_single<TASR_EPI_SILU, false, false>(a, p, st);
+      break;
+    case TASR_EPI_SWIGLU_BWD:
+      if (!am && bm) return launch_single<TASR_EPI_SWIGLU_BWD, false, true>(a, p, st);
+      break;
+    case TASR_EPI_GLU_BWD:
+      if (!am && bm) return launch_single<TASR_EPI_GLU_BWD, false, true>(a, p, st);
+      break;
+    case TASR_EPI_SILU_BWD:
+      if (!am && bm) return launch_single<TASR_EPI_SILU_BWD, false, true>(a, p, st);
+      break;
+    case TASR_EPI_ATOMIC:
+      if (am && bm) return launch_single<TASR_EPI_ATOMIC, true, true>(a, p, st);
+      break;
+    default: break;
   }
-  if (!a->a_mn_major && !a->b_mn_major) return launch_tc<128, 3, false, false, false>(a, p, st);
-  if (!a->a_mn_major && a->b_mn_major) return launch_tc<128, 3, false, true, false>(a, p, st);
-  if (a->a_mn_major && a->b_mn_major) return launch_tc<128, 3, true, true, false>(a, p, st);
-  return launch_tc<128, 3, true, false, false>(a, p, st);
+  return TASR_ERR_SHAPE;  // epilogue / operand-major combination not instantiated (see include/tasr_kernels.h)
 }
 
 extern "C" int tasr_gemm_bf16_debug(const tasr_gemm_args* a, tasr_stream_t stream) {
@@ -478,6 +714,7 @@ extern "C" int tasr_gemm_bf16_debug(const tasr_gemm_args* a, tasr_stream_t strea
   int rc = fill_dev(a, &p, &dual);
   if (rc) return rc;
   p.kb_per_split = (a->K + BK - 1) / BK;
+  p.splits = 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long total = (long long)a->M * ((a->N + 31) / 32);
   gemm_debug_kernel<<<cdiv(total, 128), 128, 0, st>>>(reinterpret_cast<const bf16*>(a->A), a->lda, a->a_mn_major,

@@ -5,6 +5,12 @@
 
 static thread_local char g_err[512] = "";
 unsigned long long g_tasr_launches = 0;
+const unsigned long long* g_tasr_seed_ptr = nullptr;
+
+extern "C" int tasr_set_dropout_seed_ptr(const uint64_t* dev_ptr) {
+  g_tasr_seed_ptr = reinterpret_cast<const unsigned long long*>(dev_ptr);
+  return TASR_OK;
+}
 
 extern "C" uint64_t tasr_launch_count(void) { return g_tasr_launches; }
 

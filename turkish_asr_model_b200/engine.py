@@ -141,7 +141,7 @@ class ConformerEngine:
         self.V = model.fc.out_features
         self.F2 = model.input_proj.in_features // self.d
         self._cos_sin = None
-        self._step_seed = 0
+        self.device_seed = False  # True: dropout seeds come from the device counter (CUDA-graph replay)
 
     # ------------------------------------------------------------------ parameters
     def ensure_flat(self):
@@ -154,21 +154,30 @@ class ConformerEngine:
         f = self.flat
         d, dff = self.d, self.dff
 
+        cache = {}
+
+        def cached(buf_id, buf, name, shape, numel):
+            key = (buf_id, name, shape, numel)
+            v = cache.get(key)
+            if v is None:
+                v = cache[key] = f.view(buf, name, shape, numel)
+            return v
+
         def P(name, shape=None, numel=None):
-            return f.view(f.params, name, shape, numel)
+            return cached(0, f.params, name, shape, numel)
 
         def S(name, shape=None, numel=None):
-            return f.view(f.shadow, name, shape, numel)
+            return cached(1, f.shadow, name, shape, numel)
 
         def G(name, shape=None, numel=None):
-            return f.view(f.grads, name, shape, numel)
+            return cached(2, f.grads, name, shape, numel)
 
         self.P, self.S, self.Gv = P, S, G
         self.qkv_w_shape = (d + 2 * DH, d)
 
     def cos_sin(self, T, device):
         if self._cos_sin is None or self._cos_sin.shape[0] < T or self._cos_sin.device != device:
-            n = max(T, 512)
+            n = max(T, 2048)
             inv_freq = self.model.blocks[0].attn.rotary_emb.inv_freq.to(device=device, dtype=torch.float32)
             t = torch.arange(n, device=device, dtype=torch.float32)
             freqs = torch.outer(t, inv_freq)  # model/attention.py:42-44
@@ -197,7 +206,7 @@ class ConformerEngine:
         cs = self.cos_sin(T2, dev)
         drop = float(dropout_p) if training else 0.0
         seed0 = 0
-        if drop > 0.0:
+        if drop > 0.0 and not self.device_seed:
             seed0 = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) * 4096
         tape = {"B": B, "T": T, "F": F, "T2": T2, "M": M, "key_len": key_len, "drop": drop, "seed0": seed0,
                 "feats": feats, "blocks": []} if save else None

@@ -30,7 +30,8 @@ class _NullLogger:
 class Trainer:
     def __init__(self, model, train_loader, optimizer, scheduler, device, config, logger, valid_loader=None,
                  tokenizer=None, gradient_clip: float = 1.0, accumulation_steps: int = 1, *, process_group=None,
-                 bucket_bytes: int = 25 << 20, preprocessor: Optional[AudioPreprocessor] = None):
+                 bucket_bytes: int = 25 << 20, preprocessor: Optional[AudioPreprocessor] = None,
+                 use_cuda_graphs: bool = True, max_graph_samples: int = 16000 * 20):
         self.model = model
         self.train_loader = train_loader
         self.valid_loader = valid_loader
@@ -62,6 +63,13 @@ class Trainer:
         self._sumsq = None
         self._norm = None
         self.last_grad_norm = None
+        # CUDA graphs: one captured step per batch shape (bucketed batches recur every epoch), shared memory pool
+        self.use_cuda_graphs = use_cuda_graphs
+        self.max_graph_samples = max_graph_samples
+        self._graphs = {}
+        self._graph_pool = None
+        self._static = None
+        self._seed_dev = None
 
     # ------------------------------------------------------------------ optimizer state on flat buffers
     def _flat(self):
@@ -73,7 +81,9 @@ class Trainer:
             self._hyper = torch.zeros(9, dtype=torch.float32, device=flat.device)
             self._sumsq = torch.zeros(1, dtype=torch.float64, device=flat.device)
             self._norm = torch.zeros(1, dtype=torch.float32, device=flat.device)
-            self._hyper_host = torch.zeros(9, dtype=torch.float32).pin_memory()
+            self._hyper_ring = [torch.zeros(9, dtype=torch.float32).pin_memory() for _ in range(16)]
+            self._seed_dev = torch.zeros(1, dtype=torch.int64, device=flat.device)
+            L.check(L.lib().tasr_set_dropout_seed_ptr(self._seed_dev.data_ptr()))
             views = flat.grad_views()
             for name, p in self.model.named_parameters():
                 if name in views:
@@ -103,6 +113,10 @@ class Trainer:
         eng, flat = self._flat()
         dev = flat.device
         self.model.train()
+        return self._step_features(eng, flat, features, targets, input_lengths, target_lengths, host_opt=True)
+
+    def _step_features(self, eng, flat, features, targets, input_lengths, target_lengths, host_opt):
+        dev = flat.device
         if self._micro == 0:
             flat.grads[: flat.live_numel].zero_()
         features = features.to(dev, non_blocking=True)
@@ -122,7 +136,9 @@ class Trainer:
         if last_micro:
             for h in handles:
                 h.wait()
-            self._optimizer_step(flat)
+            if host_opt:
+                self._optimizer_host()
+            self._optimizer_device(flat)
             self._micro = 0
         return loss[0]
 
@@ -134,8 +150,60 @@ class Trainer:
         dev = self.model.fc.weight.device
         if tmax is None and not n_samples.is_cuda:
             tmax = 1 + int(n_samples.max()) // 160
+        B, nmax = waves.shape
+        if (self.use_cuda_graphs and tmax is not None and self.world_size == 1 and self.accumulation_steps == 1
+                and nmax <= self.max_graph_samples):
+            return self._graphed_step(waves, n_samples, targets, target_lengths, tmax)
         feats, frames = self.preprocessor.extract_features_batch(waves.to(dev, non_blocking=True), n_samples, tmax)
         return self.train_step(feats, targets, frames, target_lengths)
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def _graphed_step(self, waves, n_samples, targets, target_lengths, tmax):
+        """The step is a fixed kernel sequence for a given batch shape, and bucketed batches recur every epoch,
+        so each shape is captured once (torch.cuda.graph, one shared memory pool) and replayed: ~600 kernel
+        launches collapse into one graph launch.  Per-step variation lives in device memory: the inputs (static
+        buffers), the AdamW hyper-parameters (uploaded before the replay) and the dropout seed counter."""
+        eng, flat = self._flat()
+        dev = flat.device
+        self.model.train()
+        B, nmax = waves.shape
+        smax = targets.shape[1]
+        if self._static is None or self._static["B"] != B:
+            cap = self.max_graph_samples
+            self._static = {"B": B, "waves": torch.zeros(B * cap, dtype=torch.float32, device=dev),
+                            "n": torch.zeros(B, dtype=torch.int64, device=dev),
+                            "targets": torch.zeros(B * 1024, dtype=torch.int64, device=dev),
+                            "tl": torch.zeros(B, dtype=torch.int64, device=dev)}
+            self._graphs = {}
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        if smax > 1024:
+            self.use_cuda_graphs = False
+            return self.train_step_waveforms(waves, n_samples, targets, target_lengths, tmax)
+        st = self._static
+        s_w = st["waves"][: B * nmax].view(B, nmax)
+        s_t = st["targets"][: B * smax].view(B, smax)
+        s_w.copy_(waves, non_blocking=True)
+        st["n"].copy_(n_samples, non_blocking=True)
+        s_t.copy_(targets, non_blocking=True)
+        st["tl"].copy_(target_lengths, non_blocking=True)
+        self._optimizer_host()
+        key = (B, nmax, tmax, smax)
+        entry = self._graphs.get(key)
+        if entry is None:
+            # everything that is created lazily must exist before capture
+            self.preprocessor._tables(dev)
+            eng.cos_sin(4096, dev)
+            L.workspace(1, dev)
+            flat.refresh_shadow()
+            eng.device_seed = True
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._graph_pool):
+                feats, frames = self.preprocessor.extract_features_batch(s_w, st["n"], tmax)
+                loss = self._step_features(eng, flat, feats, s_t, frames, st["tl"], host_opt=False)
+            entry = self._graphs[key] = (g, loss)
+        entry[0].replay()
+        return entry[1]
 
     def _backward_with_allreduce(self, eng, flat, tape, dlogits):
         """Backward with one asynchronous NCCL all-reduce per gradient bucket, issued as soon as the kernels
@@ -170,29 +238,39 @@ class Trainer:
         flush(force=True)
         return handles
 
-    def _optimizer_step(self, flat):
+    def _optimizer_host(self):
+        """Host half of the optimizer step: hyper-parameters of THIS step go to the device buffer the fused
+        kernel reads (pinned ring so that an in-flight copy is never overwritten), counters, LR schedule."""
         lr, b1, b2, eps, wd = self._group()
         self._opt_step += 1
         t = self._opt_step
-        h = self._hyper_host
+        h = self._hyper_ring[t % len(self._hyper_ring)]
         h[0], h[1], h[2], h[3], h[4] = lr, b1, b2, eps, wd
         h[5], h[6] = 1.0 - b1 ** t, 1.0 - b2 ** t
         h[7] = float(self.gradient_clip) if self.gradient_clip else 0.0
         h[8] = float(self.world_size)  # all-reduce sums over ranks; the mean is folded into the clip scale
         self._hyper.copy_(h, non_blocking=True)
-        self._sumsq.zero_()
-        n = flat.live_numel
-        L.grad_sumsq(flat.grads[:n], self._sumsq)
-        L.clip_adamw(flat.params[:n], flat.grads[:n], flat.exp_avg[:n], flat.exp_avg_sq[:n], flat.shadow[:n], self._hyper,
-                     self._sumsq, self._norm)
-        flat.shadow_fresh = True
-        self.last_grad_norm = self._norm
         self.global_step += 1
         if self.scheduler is not None:
             import warnings
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")  # torch warns because optimizer.step() is replaced by the fused kernel
                 self.scheduler.step()
+
+    def _optimizer_device(self, flat):
+        """Device half: global grad norm + clip + AdamW + bf16 shadow refresh (graph-capturable)."""
+        self._sumsq.zero_()
+        n = flat.live_numel
+        L.grad_sumsq(flat.grads[:n], self._sumsq)
+        L.clip_adamw(flat.params[:n], flat.grads[:n], flat.exp_avg[:n], flat.exp_avg_sq[:n], flat.shadow[:n], self._hyper,
+                     self._sumsq, self._norm)
+        self._seed_dev.add_(0x632BE59BD9B4E019)  # fresh dropout masks for the next step / graph replay
+        flat.shadow_fresh = True
+        self.last_grad_norm = self._norm
+
+    def _optimizer_step(self, flat):
+        self._optimizer_host()
+        self._optimizer_device(flat)
 
     # ------------------------------------------------------------------ epoch loops (reference API)
     def train_epoch(self, epoch: int) -> float:
