@@ -256,7 +256,7 @@ def run_gpu(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    launches0 = L.lib().tasr_launch_count()
+    launches0 = L.lib().tasr_launch_count() + trainer.graph_kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     audio = 0.0
     e0.record()
@@ -266,7 +266,7 @@ def run_gpu(args):
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
-    launches = L.lib().tasr_launch_count() - launches0
+    launches = L.lib().tasr_launch_count() + trainer.graph_kernel_launches - launches0
     final_loss = float(loss)
 
     # ---- end-to-end: pinned host buffers -> H2D -> step -> D2H of the loss, every step

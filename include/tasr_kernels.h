@@ -212,6 +212,26 @@ int tasr_col2im_conv1_bwd(const void* dcol, const float* x, int B, int T, int F,
 int tasr_pack_weight_remap(const float* in, int64_t N, int K, int q, void* out, tasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Conv2d subsampler as implicit GEMM (no im2col buffer; 4-D TMA gathers, tcgen05 main loop).
+ * Replaces: model/conformer.py:150-155,177-183 and the autograd backward of both convolutions.
+ *   conv1_fwd : x (B,T,F) fp32 -> y1 (B,T1,F1,d) bf16 NHWC = silu(conv1(x))
+ *   conv2_fwd : y1, w2p (d, 9d) bf16 packed (co,kh,kw,ci), bias (d) -> z2 (pre-activation) and
+ *               y2 = silu(z2), both (B,T2,F2,d) bf16 == the (B*T2, F2*d) operand of input_proj
+ *   conv2_dgrad: dz2 -> dy1 (B,T1,F1,d) bf16 (one GEMM per output-parity class)
+ *   conv2_wgrad: dW2 (d,d,3,3) fp32 += dz2^T (*) y1
+ *   conv1_bwd : dy1, x -> dW1 (d,1,3,3), db1 (d) fp32 (+=); conv1's pre-activation is recomputed
+ * T, F are the mel-feature dimensions; d % 128 == 0; F must reduce 80 -> 40 -> 20 style (F1 = 2*F2, F2 % 4 == 0).
+ * ---------------------------------------------------------------------------------------------- */
+int tasr_conv1_fwd(const float* x, int B, int T, int F, int d, const float* w1, const float* b1, void* y1,
+                   tasr_stream_t stream);
+int tasr_conv1_bwd(const void* dy1, const float* x, int B, int T, int F, int d, const float* w1, const float* b1,
+                   float* dw1, float* db1, tasr_stream_t stream);
+int tasr_conv2_fwd(const void* y1, int B, int T, int F, int d, const void* w2p, const float* bias, void* z2, void* y2,
+                   tasr_stream_t stream);
+int tasr_conv2_dgrad(const void* dz2, int B, int T, int F, int d, const void* w2p, void* dy1, tasr_stream_t stream);
+int tasr_conv2_wgrad(const void* dz2, const void* y1, int B, int T, int F, int d, float* dw2, tasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused log-softmax + CTC loss (mean reduction, zero_infinity) + gradient w.r.t. the logits.
  * Replaces: trainer/trainer.py:167-173 (log_softmax + nn.CTCLoss(blank=0, zero_infinity=True)) and
  *   their backward.  logits (B,T,V) bf16 or fp32 with row pitch ld >= V elements (dlogits: same pitch); targets (B,Smax) int64 padded; lengths int64 (B),

@@ -205,6 +205,51 @@ def test_conv1_im2col_and_bwd(cuda, B, T, d):
     assert rel_err(dw1, w1d.grad) < 1e-3 and rel_err(db1, b1d.grad) < 1e-3
 
 
+@pytest.mark.parametrize("B,T,d", [(2, 203, 256), (1, 130, 512), (3, 9, 256), (2, 64, 128)])
+def test_implicit_conv_subsampler(cuda, B, T, d):
+    """conv1_fwd + conv2_fwd / dgrad / wgrad + conv1_bwd (implicit GEMM) vs F.conv2d autograd in float64."""
+    Fm = 80
+    g = torch.Generator().manual_seed(T + d)
+    x = torch.randn(B, T, Fm, generator=g)
+    w1 = torch.randn(d, 1, 3, 3, generator=g) / 3
+    b1 = torch.randn(d, generator=g) / 3
+    w2 = torch.randn(d, d, 3, 3, generator=g) / (3 * d ** 0.5)
+    b2 = torch.randn(d, generator=g) / 3
+    T1, F1, T2, F2 = L.sub_dims(T, Fm)
+    w1d, b1d = w1.double().requires_grad_(True), b1.double().requires_grad_(True)
+    w2q = bf(w2).double().requires_grad_(True)
+    b2d = b2.double().requires_grad_(True)
+    y1r = F.silu(F.conv2d(x.double().unsqueeze(1), w1d, b1d, stride=2, padding=1))        # (B,d,T1,F1)
+    y1q = y1r + (y1r.detach().to(torch.bfloat16).double() - y1r.detach())                  # bf16-rounded operand
+    z2r = F.conv2d(y1q, w2q, b2d, stride=2, padding=1)                                     # (B,d,T2,F2)
+    # device
+    y1 = L.conv1_fwd(x.to(cuda), w1.to(cuda), b1.to(cuda))
+    w2p = L.pack_weight_remap(w2.view(d, 9 * d).to(cuda), 9)
+    z2, y2 = L.conv2_fwd(y1, T, Fm, w2p, b2.to(cuda))
+    torch.cuda.synchronize()
+    assert y1.shape == (B, T1, F1, d)
+    assert rel_err(y1, y1r.detach().permute(0, 2, 3, 1)) < 6e-3
+    z2_ref = z2r.detach().permute(0, 2, 3, 1).reshape(B * T2 * F2, d)
+    assert rel_err(z2, z2_ref) < 1e-2
+    assert rel_err(y2, F.silu(z2_ref)) < 1.2e-2
+    # backward
+    dz2 = bf(torch.randn(B * T2 * F2, d, generator=g))
+    z2r.backward(dz2.double().view(B, T2, F2, d).permute(0, 3, 1, 2))
+    dy1 = L.conv2_dgrad(dz2.to(cuda), B, T, Fm, w2p)
+    dw2 = torch.zeros(d, d, 3, 3, device=cuda)
+    L.conv2_wgrad(dz2.to(cuda), y1, T, Fm, dw2)
+    torch.cuda.synchronize()
+    assert rel_err(dw2, w2q.grad) < 1.5e-2
+    # dy1 reference: gradient w.r.t. the conv2 input
+    y1leaf = y1q.detach().requires_grad_(True)
+    F.conv2d(y1leaf, w2q.detach(), b2d.detach(), stride=2, padding=1).backward(dz2.double().view(B, T2, F2, d).permute(0, 3, 1, 2))
+    assert rel_err(dy1, y1leaf.grad.permute(0, 2, 3, 1)) < 1.2e-2
+    dw1, db1 = torch.zeros(d, 1, 3, 3, device=cuda), torch.zeros(d, device=cuda)
+    L.conv1_bwd(dy1, x.to(cuda), w1.to(cuda), b1.to(cuda), dw1, db1)
+    torch.cuda.synchronize()
+    assert rel_err(dw1, w1d.grad) < 1.5e-2 and rel_err(db1, b1d.grad) < 1.5e-2
+
+
 def test_pack_weight_remap(cuda):
     g = torch.Generator().manual_seed(3)
     w = torch.randn(256, 128, 3, 3, generator=g)

@@ -20,7 +20,7 @@ class Cfg:
     log_interval = 10 ** 9
 
 
-tr = Trainer(model, None, opt, None, dev, Cfg(), None)
+tr = Trainer(model, None, opt, None, dev, Cfg(), None, use_cuda_graphs=False)
 which = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 b = bench.make_batches(which + 1, 0, 1)[which]
 w = bench.synth_waves(b, dev)

@@ -46,6 +46,11 @@ _SIGNATURES = {
     "tasr_conv1_im2col": (I, [P, I, I, I, I, P, P, P, P]),
     "tasr_col2im_conv1_bwd": (I, [P, P, I, I, I, I, P, P, P, P, P]),
     "tasr_pack_weight_remap": (I, [P, L, I, I, P, P]),
+    "tasr_conv1_fwd": (I, [P, I, I, I, I, P, P, P, P]),
+    "tasr_conv1_bwd": (I, [P, P, I, I, I, I, P, P, P, P, P]),
+    "tasr_conv2_fwd": (I, [P, I, I, I, I, P, P, P, P, P]),
+    "tasr_conv2_dgrad": (I, [P, I, I, I, I, P, P, P]),
+    "tasr_conv2_wgrad": (I, [P, P, I, I, I, I, P, P]),
     "tasr_ctc_workspace_bytes": (Z, [I, I, I, I]),
     "tasr_ctc_loss_fwd_bwd": (I, [P, I, L, I, I, I, P, I, P, P, I, F, P, P, P, P, Z, P]),
     "tasr_grad_sumsq": (I, [P, L, P, P]),
@@ -337,6 +342,45 @@ def pack_weight_remap(w2d, q):
     out = torch.empty(N, K, dtype=torch.bfloat16, device=w2d.device)
     check(lib().tasr_pack_weight_remap(ptr(w2d), N, K, q, ptr(out), stream_ptr()))
     return out
+
+
+def conv1_fwd(x, w1, b1):
+    """x (B,T,F) fp32 -> y1 (B,T1,F1,d) bf16 NHWC."""
+    require_cuda(x, w1, b1)
+    B, T, F = x.shape
+    d = w1.shape[0]
+    T1, F1, _, _ = sub_dims(T, F)
+    y1 = torch.empty(B, T1, F1, d, dtype=torch.bfloat16, device=x.device)
+    check(lib().tasr_conv1_fwd(ptr(x), B, T, F, d, ptr(w1), ptr(b1), ptr(y1), stream_ptr()))
+    return y1
+
+
+def conv1_bwd(dy1, x, w1, b1, dw1, db1):
+    B, T, F = x.shape
+    check(lib().tasr_conv1_bwd(ptr(dy1), ptr(x), B, T, F, w1.shape[0], ptr(w1), ptr(b1), ptr(dw1), ptr(db1), stream_ptr()))
+
+
+def conv2_fwd(y1, T, F, w2p, bias):
+    """y1 (B,T1,F1,d) -> (z2, y2) each (B*T2*F2, d) bf16."""
+    B, _, _, d = y1.shape
+    _, _, T2, F2 = sub_dims(T, F)
+    z2 = torch.empty(B * T2 * F2, d, dtype=torch.bfloat16, device=y1.device)
+    y2 = torch.empty_like(z2)
+    check(lib().tasr_conv2_fwd(ptr(y1), B, T, F, d, ptr(w2p), ptr(bias), ptr(z2), ptr(y2), stream_ptr()))
+    return z2, y2
+
+
+def conv2_dgrad(dz2, B, T, F, w2p):
+    d = dz2.shape[-1]
+    T1, F1, _, _ = sub_dims(T, F)
+    dy1 = torch.empty(B, T1, F1, d, dtype=torch.bfloat16, device=dz2.device)
+    check(lib().tasr_conv2_dgrad(ptr(dz2), B, T, F, d, ptr(w2p), ptr(dy1), stream_ptr()))
+    return dy1
+
+
+def conv2_wgrad(dz2, y1, T, F, dw2):
+    B, _, _, d = y1.shape
+    check(lib().tasr_conv2_wgrad(ptr(dz2), ptr(y1), B, T, F, d, ptr(dw2), stream_ptr()))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -10,190 +10,12 @@
 //
 // Replaces (reference): every nn.Linear / 1x1 Conv1d / Conv2d-as-GEMM and their autograd backward, see
 // include/tasr_kernels.h.
-#include "common.cuh"
+#include "gemm_common.cuh"
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
 
 namespace {
-
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 320;       // producer warp + MMA warp + 8 epilogue warps
-constexpr int EPI_THREADS = 256;
-constexpr int EPI_GROUP_THREADS = 128;  // one epilogue group = 4 warps = the 4 TMEM lane quarters
-constexpr int STAGE_BYTES = 16384;  // 128 rows x 128 B
-
-struct GemmDev {
-  int M, N, K;
-  int epi;
-  int out_f32;
-  void* out;
-  long long ldo;
-  void* out2;
-  long long ldo2;
-  const float* bias;
-  const void* aux;
-  long long ldaux;
-  float alpha;
-  int n_half;
-  uint32_t drop_thresh;
-  float drop_inv_keep;
-  unsigned long long seed;
-  const unsigned long long* seed_ptr;
-  int kb_per_split;
-  int splits;
-  int remap_p0, remap_p1;
-  int tiles_m, tiles_n;
-};
-
-__device__ __forceinline__ void load_bf16_chunk(const bf16* src, float* v, int nvalid) {
-  if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-    const uint4* s4 = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u = s4[i];
-      float2 f;
-      f = unpack_bf16x2(u.x); v[8 * i + 0] = f.x; v[8 * i + 1] = f.y;
-      f = unpack_bf16x2(u.y); v[8 * i + 2] = f.x; v[8 * i + 3] = f.y;
-      f = unpack_bf16x2(u.z); v[8 * i + 4] = f.x; v[8 * i + 5] = f.y;
-      f = unpack_bf16x2(u.w); v[8 * i + 6] = f.x; v[8 * i + 7] = f.y;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? __bfloat162float(src[i]) : 0.f;
-  }
-}
-__device__ __forceinline__ void load_f32_chunk(const float* src, float* v, int nvalid) {
-  if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 f = s4[i];
-      v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? src[i] : 0.f;
-  }
-}
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
-
-// ------------------------------------------------------------------------------------------------
-// Fused epilogue math on one row chunk of 32 columns [col0, col0+32) of output row `row`.
-//   in : lo = accumulator;  hi = paired accumulator (dual-B modes)
-//   out: lo = primary output, hi = second output, t3 = third output (see table below)
-//     STORE / RESID / SILU_BWD / ATOMIC : lo -> out
-//     SWIGLU / GLU                      : t3 -> out (h|u), lo -> out2[:, col] (g|a), hi -> out2[:, n_half+col]
-//     SILU                              : t3 -> out (silu(z)), lo -> out2 (z)
-//     SWIGLU_BWD / GLU_BWD              : lo -> out[:, col], hi -> out[:, n_half+col]
-// Rows >= M or columns >= N produce don't-care values (clipped by the TMA store / masked by the caller).
-// The mode is a template parameter: only that mode's code is generated (the step is epilogue-bound for
-// the K = 256 GEMMs, and one 32-column chunk of a generic switch was ~15k SASS instructions).
-// ------------------------------------------------------------------------------------------------
-template <int EPI>
-__device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col0, float* lo, float* hi, float* t3) {
-  const int nvalid = (row < p.M) ? max(0, min(32, p.N - col0)) : 0;
-  const long long r = row;
-  const unsigned long long seed = (p.drop_thresh && p.seed_ptr) ? p.seed + *p.seed_ptr : p.seed;
-  const unsigned long long idx0 = (unsigned long long)(r * p.N + col0);  // even: N is even when dropout is on
-  if (EPI == TASR_EPI_STORE) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float b = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
-      lo[i] = p.alpha * (lo[i] + b);
-    }
-  } else if (EPI == TASR_EPI_RESID) {
-    load_f32_chunk(reinterpret_cast<const float*>(p.aux) + r * p.ldaux + col0, t3, nvalid);
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const float b0 = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
-      const float b1 = (p.bias != nullptr && i + 1 < nvalid) ? p.bias[col0 + i + 1] : 0.f;
-      float v0 = lo[i] + b0, v1 = lo[i + 1] + b1;
-      if (p.drop_thresh) {
-        float s0, s1;
-        dropout_scale2(seed, idx0 + i, p.drop_thresh, p.drop_inv_keep, s0, s1);
-        v0 *= s0; v1 *= s1;
-      }
-      lo[i] = t3[i] + p.alpha * v0;
-      lo[i + 1] = t3[i + 1] + p.alpha * v1;
-    }
-  } else if (EPI == TASR_EPI_SWIGLU || EPI == TASR_EPI_GLU) {
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float s0 = 1.f, s1 = 1.f;
-      if (p.drop_thresh) dropout_scale2(seed, idx0 + i, p.drop_thresh, p.drop_inv_keep, s0, s1);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int k = i + j;
-        const float b0 = (p.bias != nullptr && k < nvalid) ? p.bias[col0 + k] : 0.f;
-        const float b1 = (p.bias != nullptr && k < nvalid) ? p.bias[p.n_half + col0 + k] : 0.f;
-        lo[k] = bf16_round(lo[k] + b0);
-        hi[k] = bf16_round(hi[k] + b1);
-        const float v = (EPI == TASR_EPI_SWIGLU) ? siluf_(lo[k]) * hi[k] : lo[k] * sigmoidf_(hi[k]);
-        t3[k] = v * (j == 0 ? s0 : s1);
-      }
-    }
-  } else if (EPI == TASR_EPI_SILU) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float b = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
-      lo[i] = bf16_round(lo[i] + b);
-      t3[i] = siluf_(lo[i]);
-    }
-  } else if (EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) {
-    const bf16* ax = reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux;
-    load_bf16_chunk(ax + col0, hi, nvalid);             // g | a
-    load_bf16_chunk(ax + p.n_half + col0, t3, nvalid);  // v | b
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float s0 = 1.f, s1 = 1.f;
-      if (p.drop_thresh) dropout_scale2(seed, idx0 + i, p.drop_thresh, p.drop_inv_keep, s0, s1);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int k = i + j;
-        const float d = lo[k] * (j == 0 ? s0 : s1);
-        const float g = hi[k], v = t3[k];
-        if (EPI == TASR_EPI_SWIGLU_BWD) {
-          const float sg = sigmoidf_(g);
-          lo[k] = d * v * sg * (1.f + g * (1.f - sg));  // d/dg
-          hi[k] = d * g * sg;                            // d/dv
-        } else {
-          const float sv = sigmoidf_(v);
-          lo[k] = d * sv;                                // d/da
-          hi[k] = d * g * sv * (1.f - sv);               // d/db
-        }
-      }
-    }
-  } else if (EPI == TASR_EPI_SILU_BWD) {
-    load_bf16_chunk(reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux + col0, t3, nvalid);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) lo[i] = lo[i] * silu_gradf_(t3[i]);
-  } else if (EPI == TASR_EPI_ATOMIC) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) lo[i] *= p.alpha;
-  }
-}
-
-// staging writes: row r of a [128 rows x 128 B] buffer in the TMA 128-byte swizzle
-__device__ __forceinline__ void stage_bf16_half(uint8_t* buf, int r, int half, const float* v) {
-  uint8_t* base = buf + r * 128;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-    *reinterpret_cast<uint4*>(base + (((half * 4 + i) ^ (r & 7)) << 4)) = u;
-  }
-}
-__device__ __forceinline__ void stage_f32(uint8_t* buf, int r, const float* v) {
-  uint8_t* base = buf + r * 128;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    *reinterpret_cast<float4*>(base + ((i ^ (r & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
 
 // ------------------------------------------------------------------------------------------------
 // the kernel

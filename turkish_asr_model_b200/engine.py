@@ -214,17 +214,15 @@ class ConformerEngine:
         # ---- subsampler (model/conformer.py:177-185)
         w2p = L.pack_weight_remap(P("subsample.2.weight").view(d, 9 * d), 9)
         winp = L.pack_weight_remap(P("input_proj.weight"), F2)
-        col = L.conv1_im2col(feats, P("subsample.0.weight"), P("subsample.0.bias"))
-        Mpix = col.shape[0]
-        z2 = torch.empty(Mpix, d, dtype=torch.bfloat16, device=dev) if save else None
-        y2 = torch.empty(Mpix, d, dtype=torch.bfloat16, device=dev)
-        L.gemm(Mpix, d, 9 * d, col, 9 * d, w2p, 9 * d, L.EPI_SILU, y2, d, out2=z2, ldo2=d, bias=P("subsample.2.bias"))
+        # conv1 (K = 9) direct to NHWC bf16; conv2 as implicit GEMM on tcgen05 (4-D TMA gathers, SiLU epilogue)
+        y1 = L.conv1_fwd(feats, P("subsample.0.weight"), P("subsample.0.bias"))
+        z2, y2 = L.conv2_fwd(y1, T, F, w2p, P("subsample.2.bias"))
         x = torch.empty(M, d, dtype=torch.float32, device=dev)
         L.gemm(M, d, F2 * d, y2, F2 * d, winp, F2 * d, L.EPI_STORE, x, d, out_f32=1, bias=P("input_proj.bias"))
         if save:
-            tape.update(col=col, z2=z2, y2=y2, w2p=w2p, winp=winp)
+            tape.update(y1=y1, z2=z2, y2=y2, w2p=w2p, winp=winp)
         else:
-            del col
+            del y1, z2
 
         for i in range(self.n_blocks):
             x = self._block_forward(i, x, B, T2, key_len, cs, training, drop, seed0 + i * 16, tape)
@@ -418,11 +416,10 @@ class ConformerEngine:
         dz2 = torch.empty(Mpix, d, dtype=torch.bfloat16, device=dev)
         L.gemm(M, F2 * d, d, dx0, d, tape["winp"], F2 * d, L.EPI_SILU_BWD, dz2, F2 * d, b_mn=1, aux=tape["z2"],
                ldaux=F2 * d)
-        self._wgrad(dz2, tape["col"], d, 9 * d, Mpix, Gv("subsample.2.weight").view(d, 9 * d), remap=(d, 9))
+        L.conv2_wgrad(dz2, tape["y1"], tape["T"], tape["F"], Gv("subsample.2.weight"))
         L.colsum_add(dz2, Gv("subsample.2.bias"))
-        dcol = torch.empty(Mpix, 9 * d, dtype=torch.bfloat16, device=dev)
-        L.gemm(Mpix, 9 * d, d, dz2, d, tape["w2p"], 9 * d, L.EPI_STORE, dcol, 9 * d, b_mn=1)
-        L.col2im_conv1_bwd(dcol, tape["feats"], P("subsample.0.weight"), P("subsample.0.bias"),
-                           Gv("subsample.0.weight"), Gv("subsample.0.bias"))
+        dy1 = L.conv2_dgrad(dz2, B, tape["T"], tape["F"], tape["w2p"])
+        L.conv1_bwd(dy1, tape["feats"], P("subsample.0.weight"), P("subsample.0.bias"),
+                    Gv("subsample.0.weight"), Gv("subsample.0.bias"))
         if on_segment_done is not None:
             on_segment_done(1 + self.n_blocks)

@@ -70,6 +70,7 @@ class Trainer:
         self._graph_pool = None
         self._static = None
         self._seed_dev = None
+        self.graph_kernel_launches = 0  # kernels executed through graph replays (bench.py's gpu_launches)
 
     # ------------------------------------------------------------------ optimizer state on flat buffers
     def _flat(self):
@@ -198,11 +199,13 @@ class Trainer:
             eng.device_seed = True
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = L.lib().tasr_launch_count()
             with torch.cuda.graph(g, pool=self._graph_pool):
                 feats, frames = self.preprocessor.extract_features_batch(s_w, st["n"], tmax)
                 loss = self._step_features(eng, flat, feats, s_t, frames, st["tl"], host_opt=False)
-            entry = self._graphs[key] = (g, loss)
+            entry = self._graphs[key] = (g, loss, L.lib().tasr_launch_count() - n0)
         entry[0].replay()
+        self.graph_kernel_launches += entry[2]
         return entry[1]
 
     def _backward_with_allreduce(self, eng, flat, tape, dlogits):
