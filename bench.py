@@ -217,7 +217,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     L.lib()
 
     torch.manual_seed(0)
@@ -231,7 +232,8 @@ def run_gpu(args):
     trainer = Trainer(model, None, opt, sched, dev, Cfg(), None, gradient_clip=1.0, accumulation_steps=1)
 
     K, W = args.steps, args.warmup
-    n_distinct = min(K + W, 12)
+    # every distinct batch shape is seen (and its CUDA graph captured) during warm-up
+    n_distinct = max(1, min(K + W, 12, W))
     batches = make_batches(n_distinct, rank, world)
     dev_batches = []
     for b in batches:
@@ -321,6 +323,7 @@ def run_gpu(args):
         # replayed back to back as ONE CUDA graph between two CUDA events: device time of exactly those kernels,
         # no host launch gaps.
         trainer.use_cuda_graphs = False
+        trainer.world_size = 1  # rank-local pass: no collectives (the other ranks are not in this branch)
         L.GEMM_PROFILE = []
         resident_step(0)
         torch.cuda.synchronize()
