@@ -7,7 +7,8 @@ data/dataset.py:283-312: collate pads features/targets with zeros and returns th
 import random
 
 
-def bucketing_order(lengths, batch_size, shuffle=True, drop_last=False, rng=random):
+def bucketing_buckets(lengths, batch_size, shuffle=True, drop_last=False, rng=random):
+    """The shuffled list of buckets (data/dataset.py:151-163)."""
     indices = sorted(range(len(lengths)), key=lambda i: lengths[i])
     batches = []
     for i in range(0, len(indices), batch_size):
@@ -16,7 +17,12 @@ def bucketing_order(lengths, batch_size, shuffle=True, drop_last=False, rng=rand
             batches.append(batch)
     if shuffle:
         rng.shuffle(batches)
-    return [i for b in batches for i in b]
+    return batches
+
+
+def bucketing_order(lengths, batch_size, shuffle=True, drop_last=False, rng=random):
+    """Flat index stream the sampler yields (data/dataset.py:165-167)."""
+    return [i for b in bucketing_buckets(lengths, batch_size, shuffle, drop_last, rng) for i in b]
 
 
 def dataloader_batches(flat, batch_size):
