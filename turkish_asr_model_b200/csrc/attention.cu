@@ -52,8 +52,9 @@ __device__ __forceinline__ void store_tile_chunk(uint8_t* tile, int r, int c0, c
   }
 }
 
+// dropout index space: rows of even pitch so that (key, key + 1) pairs share one hash in forward and backward
 __device__ __forceinline__ unsigned long long drop_index(int b, int h, int H, int T, int q, int k) {
-  return (((unsigned long long)(b * H + h) * T + q) * (unsigned long long)T) + k;
+  return (((unsigned long long)(b * H + h) * T + q) * (unsigned long long)((T + 1) & ~1)) + k;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -227,40 +228,53 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ dctx, const bf16* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: grid (ceil(T/128) kv blocks, B); loops over heads and query tiles
+// backward: grid (ceil(T/128) kv blocks, B); loops over heads and query tiles.
+// 256 threads: warps 0-3 own columns [0,64) of the S / dP tiles, warps 4-7 columns [64,128) (one TMEM lane =
+// one query row per thread pair).  Q / dO tiles are double-buffered: the TMA for iteration it+1 is in flight
+// while iteration it runs.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ATT_THREADS) mqa_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv,
-                                                              const __grid_constant__ CUtensorMap tm_do, const AttnParams p) {
+constexpr int ATT_BWD_THREADS = 256;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_BWD_THREADS) mqa_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+                                                                  const __grid_constant__ CUtensorMap tm_do, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;             // 16 KB
   uint8_t* sV = smem + 16384;     // 16 KB
-  uint8_t* sQ = smem + 32768;     // 16 KB
-  uint8_t* sDO = smem + 49152;    // 16 KB
-  uint8_t* sP = smem + 65536;     // 32 KB
-  uint8_t* sDS = smem + 98304;    // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 131072);  // kv, qdo, mma1, mma2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint8_t* sQ = smem + 32768;     // 2 x 16 KB
+  uint8_t* sDO = smem + 65536;    // 2 x 16 KB
+  uint8_t* sP = smem + 98304;     // 32 KB
+  uint8_t* sDS = smem + 131072;   // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 163840);  // kv, q0, q1, mma1, mma2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int rloc = quarter * 32 + lane;  // TMEM lane = row of the tile
   const int j = blockIdx.x, b = blockIdx.y;
   const int k0 = j * BKV;
   const int Lk = p.key_len ? (int)min((long long)p.T, p.key_len[b]) : p.T;
   const int ld = p.d + 2 * DH;
-  const int krow = k0 + tid;
+  const int krow = k0 + rloc;
 
   if (k0 >= Lk) {  // fully masked key block: zero gradients
     if (krow < p.T) {
-      uint4* dst = reinterpret_cast<uint4*>(p.dqkv + ((long long)b * p.T + krow) * ld + p.d);
+      uint4* dst = reinterpret_cast<uint4*>(p.dqkv + ((long long)b * p.T + krow) * ld + p.d) + half * 8;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) dst[i] = make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
     }
     return;
   }
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -269,129 +283,142 @@ __global__ void __launch_bounds__(ATT_THREADS) mqa_bwd_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
 
+  const int nq = (p.T + BQ - 1) / BQ;
+  const int niter = p.H * nq;
+  auto issue_qdo = [&](int it) {  // thread 0 only
+    const int h = it / nq, q0 = (it - h * nq) * BQ, buf = it & 1;
+    uint64_t* bar = &bars[1 + buf];
+    mbar_expect_tx(bar, 32768);
+    tma_load_3d(sQ + buf * 16384, &tm_qkv, bar, h * DH, q0, b);
+    tma_load_3d(sQ + buf * 16384 + 8192, &tm_qkv, bar, h * DH, q0 + 64, b);
+    tma_load_3d(sDO + buf * 16384, &tm_do, bar, h * DH, q0, b);
+    tma_load_3d(sDO + buf * 16384 + 8192, &tm_do, bar, h * DH, q0 + 64, b);
+  };
   if (tid == 0) {
     mbar_expect_tx(&bars[0], 32768);
     tma_load_3d(sK, &tm_qkv, &bars[0], p.d, k0, b);
     tma_load_3d(sK + 8192, &tm_qkv, &bars[0], p.d, k0 + 64, b);
     tma_load_3d(sV, &tm_qkv, &bars[0], p.d + DH, k0, b);
     tma_load_3d(sV + 8192, &tm_qkv, &bars[0], p.d + DH, k0 + 64, b);
+    issue_qdo(0);
   }
   const unsigned long long dseed = (p.drop_thresh && p.seed_ptr) ? p.seed + *p.seed_ptr : p.seed;
   const float scale2 = p.scale * LOG2E;
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);     // Q K^T, dO V^T
   constexpr uint32_t idesc_t = umma_idesc_bf16(128, DH, 1, 1);      // P^T dO, dS^T Q
   constexpr uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);      // dS K
-  const int nq = (p.T + BQ - 1) / BQ;
-  int it = 0;
-  for (int h = 0; h < p.H; ++h) {
-    for (int qi = 0; qi < nq; ++qi, ++it) {
-      const uint32_t ph = (uint32_t)it & 1u;
-      const int q0 = qi * BQ;
-      if (tid == 0) {
-        mbar_expect_tx(&bars[1], 32768);
-        tma_load_3d(sQ, &tm_qkv, &bars[1], h * DH, q0, b);
-        tma_load_3d(sQ + 8192, &tm_qkv, &bars[1], h * DH, q0 + 64, b);
-        tma_load_3d(sDO, &tm_do, &bars[1], h * DH, q0, b);
-        tma_load_3d(sDO + 8192, &tm_do, &bars[1], h * DH, q0 + 64, b);
-        if (it == 0) mbar_wait(&bars[0], 0);
-        mbar_wait(&bars[1], ph);
-        tc_fence_after();
-        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), da = smem_u32(sDO), va = smem_u32(sV);
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_bf16(tS, umma_desc_sw128(qa + k * 32, 16, 1024), umma_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_bf16(tDP, umma_desc_sw128(da + k * 32, 16, 1024), umma_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
-        umma_commit(&bars[2]);
-      }
-      const int qrow = q0 + tid;
-      const bool qvalid = qrow < p.T;
-      float lse2 = 0.f, delta = 0.f;
-      if (qvalid) {
-        lse2 = p.lse2[((long long)b * p.H + h) * p.T + qrow];
-        delta = p.delta[((long long)b * p.H + h) * p.T + qrow];
-      }
-      mbar_wait(&bars[2], ph);
-      __syncwarp();
+  const int Tp = (p.T + 1) & ~1;  // even row pitch of the dropout index space
+
+  for (int it = 0; it < niter; ++it) {
+    const int h = it / nq, qi = it - h * nq;
+    const int buf = it & 1;
+    const uint32_t ph = (uint32_t)it & 1u;          // mma barriers complete once per iteration
+    const uint32_t qph = (uint32_t)(it >> 1) & 1u;  // each q/dO buffer completes every other iteration
+    const int q0 = qi * BQ;
+    uint8_t* cQ = sQ + buf * 16384;
+    uint8_t* cDO = sDO + buf * 16384;
+    if (tid == 0) {
+      if (it + 1 < niter) issue_qdo(it + 1);  // the other buffer was released by the end of iteration it-1
+      if (it == 0) mbar_wait(&bars[0], 0);
+      mbar_wait(&bars[1 + buf], qph);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t us[32], ud[32];
-        tmem_ld32(tS + lane_addr + c * 32, us);
-        tmem_ld32(tDP + lane_addr + c * 32, ud);
-        tmem_ld_wait();
-        float pv[32], dsv[32];
+      const uint32_t qa = smem_u32(cQ), ka = smem_u32(sK), da = smem_u32(cDO), va = smem_u32(sV);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int key = k0 + c * 32 + i;
-          float pr = 0.f, ds = 0.f;
-          if (qvalid && key < Lk && lse2 != -INFINITY) {
-            pr = exp2f(__uint_as_float(us[i]) * scale2 - lse2);
-            float dp = __uint_as_float(ud[i]);
-            if (p.drop_thresh) {
-              const float ms = dropout_scale(dseed, drop_index(b, h, p.H, p.T, qrow, key), p.drop_thresh, p.drop_inv_keep);
-              dp *= ms;
-              ds = pr * (dp - delta) * p.scale;
-              pr *= ms;
-            } else {
-              ds = pr * (dp - delta) * p.scale;
-            }
-          }
-          pv[i] = pr;
-          dsv[i] = ds;
-        }
-        store_tile_chunk(sP, tid, c * 32, pv);
-        store_tile_chunk(sDS, tid, c * 32, dsv);
-      }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t pa = smem_u32(sP), sa = smem_u32(sDS), qa = smem_u32(sQ), da = smem_u32(sDO), ka = smem_u32(sK);
+      for (int k = 0; k < DH / 16; ++k)
+        umma_bf16(tS, umma_desc_sw128(qa + k * 32, 16, 1024), umma_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < BQ / 16; ++k)  // dV += P^T dO   (reduction over query rows)
-          umma_bf16(tDV, umma_desc_sw128(pa + k * 2048, 16384, 1024), umma_desc_sw128(da + k * 2048, 8192, 1024), idesc_t,
-                    (it > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < BQ / 16; ++k)  // dK += dS^T Q
-          umma_bf16(tDK, umma_desc_sw128(sa + k * 2048, 16384, 1024), umma_desc_sw128(qa + k * 2048, 8192, 1024), idesc_t,
-                    (it > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)  // dQ = dS K    (reduction over keys)
-          umma_bf16(tDQ, umma_desc_sw128(sa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                    umma_desc_sw128(ka + k * 2048, 8192, 1024), idesc_q, k > 0);
-        umma_commit(&bars[3]);
-      }
-      mbar_wait(&bars[3], ph);
-      __syncwarp();
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < DH / 32; ++c) {
-        uint32_t u[32];
-        tmem_ld32(tDQ + lane_addr + c * 32, u);
-        tmem_ld_wait();
-        if (qvalid) {
-          float* dst = p.dq_acc + ((long long)b * p.T + qrow) * p.d + h * DH + c * 32;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(u[i]));
-        }
-      }
-      tc_fence_before();
-      __syncthreads();
+      for (int k = 0; k < DH / 16; ++k)
+        umma_bf16(tDP, umma_desc_sw128(da + k * 32, 16, 1024), umma_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
+      umma_commit(&bars[3]);
     }
-  }
-  // dK, dV of this key block (summed over heads and query tiles)
-  {
-    bf16* dst = p.dqkv + ((long long)b * p.T + krow) * ld + p.d;
+    const int qrow = q0 + rloc;
+    const bool qvalid = qrow < p.T;
+    float lse2 = 0.f, delta = 0.f;
+    if (qvalid) {
+      lse2 = p.lse2[((long long)b * p.H + h) * p.T + qrow];
+      delta = p.delta[((long long)b * p.H + h) * p.T + qrow];
+    }
+    const bool row_ok = qvalid && lse2 != -INFINITY;
+    const unsigned long long drow = ((unsigned long long)(b * p.H + h) * p.T + qrow) * (unsigned long long)Tp;
+    mbar_wait(&bars[3], ph);
+    __syncwarp();
+    tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = half * 2 + cc;  // 32-column chunk of the 128-key tile
+      uint32_t us[32], ud[32];
+      tmem_ld32(tS + lane_addr + c * 32, us);
+      tmem_ld32(tDP + lane_addr + c * 32, ud);
+      tmem_ld_wait();
+      float pv[32], dsv[32];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {  // c 0,1: dK ; 2,3: dV
+      for (int i = 0; i < 32; i += 2) {
+        const int key = k0 + c * 32 + i;
+        float s0 = 1.f, s1 = 1.f;
+        if (p.drop_thresh) dropout_scale2(dseed, drow + key, p.drop_thresh, p.drop_inv_keep, s0, s1);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          float pr = 0.f, ds = 0.f;
+          if (row_ok && key + jj < Lk) {
+            const float ms = jj == 0 ? s0 : s1;
+            pr = fast_exp2(__uint_as_float(us[i + jj]) * scale2 - lse2);
+            ds = pr * (__uint_as_float(ud[i + jj]) * ms - delta) * p.scale;
+            pr *= ms;
+          }
+          pv[i + jj] = pr;
+          dsv[i + jj] = ds;
+        }
+      }
+      store_tile_chunk(sP, rloc, c * 32, pv);
+      store_tile_chunk(sDS, rloc, c * 32, dsv);
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t pa = smem_u32(sP), sa = smem_u32(sDS), qa = smem_u32(cQ), da = smem_u32(cDO), ka = smem_u32(sK);
+#pragma unroll
+      for (int k = 0; k < BQ / 16; ++k)  // dV += P^T dO   (reduction over query rows)
+        umma_bf16(tDV, umma_desc_sw128(pa + k * 2048, 16384, 1024), umma_desc_sw128(da + k * 2048, 8192, 1024), idesc_t,
+                  (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < BQ / 16; ++k)  // dK += dS^T Q
+        umma_bf16(tDK, umma_desc_sw128(sa + k * 2048, 16384, 1024), umma_desc_sw128(qa + k * 2048, 8192, 1024), idesc_t,
+                  (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < BKV / 16; ++k)  // dQ = dS K    (reduction over keys)
+        umma_bf16(tDQ, umma_desc_sw128(sa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                  umma_desc_sw128(ka + k * 2048, 8192, 1024), idesc_q, k > 0);
+      umma_commit(&bars[4]);
+    }
+    mbar_wait(&bars[4], ph);
+    __syncwarp();
+    tc_fence_after();
+    {
       uint32_t u[32];
-      const uint32_t col = (c < 2) ? (tDK + c * 32) : (tDV + (c - 2) * 32);
-      tmem_ld32(col + lane_addr, u);
+      tmem_ld32(tDQ + lane_addr + half * 32, u);
+      tmem_ld_wait();
+      if (qvalid) {
+        float4* dst = reinterpret_cast<float4*>(p.dq_acc + ((long long)b * p.T + qrow) * p.d + h * DH + half * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          atomicAdd(dst + i, make_float4(__uint_as_float(u[4 * i]), __uint_as_float(u[4 * i + 1]),
+                                         __uint_as_float(u[4 * i + 2]), __uint_as_float(u[4 * i + 3])));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  // dK, dV of this key block (summed over heads and query tiles); half 0 writes dK, half 1 writes dV
+  {
+    bf16* dst = p.dqkv + ((long long)b * p.T + krow) * ld + p.d + half * DH;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t u[32];
+      tmem_ld32((half == 0 ? tDK : tDV) + c * 32 + lane_addr, u);
       tmem_ld_wait();
       if (krow < p.T) {
 #pragma unroll
@@ -531,7 +558,7 @@ extern "C" int tasr_mqa_attention_bwd(const void* qkv, const void* ctx, const vo
   p.delta = delta;
   p.dq_acc = dq_acc;
   p.dqkv = reinterpret_cast<bf16*>(dqkv);
-  constexpr int SMEM = 131072 + 64 + 1024;
+  constexpr int SMEM = 163840 + 64 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     e = cudaFuncSetAttribute(mqa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -539,7 +566,7 @@ extern "C" int tasr_mqa_attention_bwd(const void* qkv, const void* ctx, const vo
     attr_done = true;
   }
   dim3 grid(cdiv(T, BKV), B);
-  mqa_bwd_kernel<<<grid, ATT_THREADS, SMEM, st>>>(tm_qkv, tm_do, p);
+  mqa_bwd_kernel<<<grid, ATT_BWD_THREADS, SMEM, st>>>(tm_qkv, tm_do, p);
   TASR_CHECK_LAUNCH();
   const long long total = (long long)B * T * ((d + DH) / 2);
   attn_dq_finalize_kernel<<<(int)imin64((long long)148 * 8, (total + 255) / 256), 256, 0, st>>>(
