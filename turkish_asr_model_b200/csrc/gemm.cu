@@ -473,13 +473,22 @@ int launch_tc(const tasr_gemm_args* a, GemmDev& p, cudaStream_t st) {
   return TASR_OK;
 }
 
-// tile width: wide tiles when they divide N (or N is large); they halve the shared-memory traffic per flop
-inline bool use_wide(int N) { return (N % 256 == 0) || (N > 512 && (N % 256) > 128); }
+// Tile width.  Wide (256) tiles halve the shared-memory traffic per flop, but with ~148 persistent CTAs the number
+// of scheduling rounds is what counts for the small GEMMs of this model: pick the width with fewer
+// (rounds x tile width), ties to the wide tile.
+inline bool use_wide(int M, int N, int splits) {
+  if (!((N % 256 == 0) || (N > 512 && (N % 256) > 128))) return false;
+  const long long tm = (M + BM - 1) / BM;
+  const long long wide_tiles = tm * ((N + 255) / 256) * splits, narrow_tiles = tm * ((N + 127) / 128) * splits;
+  const long long sms = g_num_sms > 0 ? g_num_sms : 148;
+  const long long cost_wide = ((wide_tiles + sms - 1) / sms) * 256, cost_narrow = ((narrow_tiles + sms - 1) / sms) * 128;
+  return cost_wide <= cost_narrow;
+}
 
 template <int EPI, bool A_MN, bool B_MN>
 int launch_single(const tasr_gemm_args* a, GemmDev& p, cudaStream_t st) {
   constexpr int R = (EPI == TASR_EPI_SILU || EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) ? 2 : 2;
-  if (use_wide(a->N)) return launch_tc<EPI, 256, 3, R, A_MN, B_MN>(a, p, st);
+  if (use_wide(a->M, a->N, p.splits)) return launch_tc<EPI, 256, 3, R, A_MN, B_MN>(a, p, st);
   return launch_tc<EPI, 128, 4, R, A_MN, B_MN>(a, p, st);
 }
 

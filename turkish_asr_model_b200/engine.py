@@ -122,9 +122,11 @@ class _W:
 
 
 def _split_k(out_f, in_f, tokens):
-    tiles = ((out_f + 127) // 128) * ((in_f + 127) // 128)
+    """Split the token reduction of a wgrad so that one wave of ~148 CTAs covers it: more splits only multiply the
+    fp32 reduce-add traffic into the (small) weight-gradient tile."""
+    tiles = ((out_f + 127) // 128) * ((in_f + 255) // 256)
     kb = (tokens + 63) // 64
-    return max(1, min(kb, (444 + tiles - 1) // tiles))
+    return max(1, min(kb, 148 // max(tiles, 1)))
 
 
 class ConformerEngine:
