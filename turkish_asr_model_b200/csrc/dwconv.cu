@@ -91,91 +91,101 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const bf16* __re
   }
 }
 
-// Backward: du = corr(dw, flipped weight); fused GLU backward -> dab (M, 2d);  dweight/dbias by atomics.
-// One CTA owns (64 channels, utterance b, a segment of time tiles) and keeps the weight-gradient
-// accumulators in registers across its tiles, so shared/global atomics happen once per CTA.
-__global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(const bf16* __restrict__ dwv, const bf16* __restrict__ u,
-                                                                const bf16* __restrict__ ab, int T, int d,
-                                                                const float* __restrict__ weight, bf16* __restrict__ dab,
-                                                                bf16* __restrict__ du_out, float* __restrict__ dweight,
-                                                                float* __restrict__ dbias, int tiles_per_cta) {
-  __shared__ __align__(16) bf162 tile[ROWS][CC / 2];   // dw with halo, then u with halo
-  __shared__ float red[CC][KW + 1];
-  const int c0 = blockIdx.x * CC, b = blockIdx.z;
+// Backward, kernel A: du = corr(dw, flipped weight) with the GLU backward fused -> dab (M, 2d) (or du).
+__global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_data_kernel(const bf16* __restrict__ dwv, const bf16* __restrict__ ab,
+                                                                     int T, int d, const float* __restrict__ weight,
+                                                                     bf16* __restrict__ dab, bf16* __restrict__ du_out) {
+  __shared__ __align__(16) bf162 tile[ROWS][CC / 2];
+  const int c0 = blockIdx.x * CC, t0 = blockIdx.y * TT, b = blockIdx.z;
   const int lane = threadIdx.x & 31, strip = threadIdx.x >> 5;
   const int ch = c0 + 2 * lane;
-  for (int i = threadIdx.x; i < CC * (KW + 1); i += DW_THREADS) (&red[0][0])[i] = 0.f;
+  load_tile(tile, dwv, b, T, d, t0, c0);
   float2 wreg[KW];
 #pragma unroll
   for (int k = 0; k < KW; ++k) wreg[k] = make_float2(weight[ch * KW + k], weight[(ch + 1) * KW + k]);
-  float2 wacc[KW];
+  __syncthreads();
+  float2 acc[OPT];
 #pragma unroll
-  for (int k = 0; k < KW; ++k) wacc[k] = make_float2(0.f, 0.f);
+  for (int o = 0; o < OPT; ++o) acc[o] = make_float2(0.f, 0.f);
+  conv_strip<true>(tile, lane, strip, wreg, acc);
+#pragma unroll
+  for (int o = 0; o < OPT; ++o) {
+    const int t = t0 + strip * OPT + o;
+    if (t < T) {
+      const long long row = (long long)b * T + t;
+      if (ab != nullptr) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + ch));
+        const float2 gt = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + d + ch));
+        const float s0 = sigmoidf_(gt.x), s1 = sigmoidf_(gt.y);
+        *reinterpret_cast<bf162*>(dab + row * 2 * d + ch) = __floats2bfloat162_rn(acc[o].x * s0, acc[o].y * s1);
+        *reinterpret_cast<bf162*>(dab + row * 2 * d + d + ch) =
+            __floats2bfloat162_rn(acc[o].x * a.x * s0 * (1.f - s0), acc[o].y * a.y * s1 * (1.f - s1));
+      }
+      if (du_out != nullptr)
+        *reinterpret_cast<bf162*>(du_out + row * d + ch) = __floats2bfloat162_rn(acc[o].x, acc[o].y);
+    }
+  }
+}
+
+// Backward, kernel B: dweight[c][k] += sum_t dw[t,c] * u[t+k-15,c], dbias[c] += sum_t dw[t,c].
+// lane = channel pair, warp w = taps 4w..4w+3 (sliding 4-value window over u); a CTA walks a segment of time tiles
+// with the accumulators in registers and issues its atomics once.
+__global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_weight_kernel(const bf16* __restrict__ dwv, const bf16* __restrict__ u,
+                                                                       int T, int d, float* __restrict__ dweight,
+                                                                       float* __restrict__ dbias, int tiles_per_cta) {
+  __shared__ __align__(16) bf162 utile[ROWS][CC / 2];
+  __shared__ __align__(16) bf162 gtile[TT][CC / 2];
+  const int c0 = blockIdx.x * CC, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ch = c0 + 2 * lane;
+  const int tap0 = 4 * w;
+  float2 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
   float2 gsum = make_float2(0.f, 0.f);
   const int ntiles = (T + TT - 1) / TT;
   const int tile_begin = blockIdx.y * tiles_per_cta, tile_end = min(ntiles, tile_begin + tiles_per_cta);
   for (int ti = tile_begin; ti < tile_end; ++ti) {
     const int t0 = ti * TT;
     __syncthreads();
-    load_tile(tile, dwv, b, T, d, t0, c0);
-    __syncthreads();
-    float2 acc[OPT];
-#pragma unroll
-    for (int o = 0; o < OPT; ++o) acc[o] = make_float2(0.f, 0.f);
-    conv_strip<true>(tile, lane, strip, wreg, acc);
-    float2 g[OPT];  // this thread's own dw values (centre rows) for the weight gradient
-#pragma unroll
-    for (int o = 0; o < OPT; ++o) {
-      g[o] = __bfloat1622float2(tile[HALO + strip * OPT + o][lane]);
-      gsum.x += g[o].x; gsum.y += g[o].y;
-    }
-#pragma unroll
-    for (int o = 0; o < OPT; ++o) {
-      const int t = t0 + strip * OPT + o;
-      if (t < T) {
-        const long long row = (long long)b * T + t;
-        if (ab != nullptr) {
-          const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + ch));
-          const float2 gt = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + d + ch));
-          const float s0 = sigmoidf_(gt.x), s1 = sigmoidf_(gt.y);
-          *reinterpret_cast<bf162*>(dab + row * 2 * d + ch) = __floats2bfloat162_rn(acc[o].x * s0, acc[o].y * s1);
-          *reinterpret_cast<bf162*>(dab + row * 2 * d + d + ch) =
-              __floats2bfloat162_rn(acc[o].x * a.x * s0 * (1.f - s0), acc[o].y * a.y * s1 * (1.f - s1));
-        }
-        if (du_out != nullptr)
-          *reinterpret_cast<bf162*>(du_out + row * d + ch) = __floats2bfloat162_rn(acc[o].x, acc[o].y);
-      }
+    load_tile(utile, u, b, T, d, t0, c0);
+    for (int i = threadIdx.x; i < TT * 8; i += DW_THREADS) {
+      const int r = i >> 3, v = i & 7;
+      const int t = t0 + r;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (t < T) val = *reinterpret_cast<const uint4*>(dwv + ((long long)b * T + t) * d + c0 + v * 8);
+      *reinterpret_cast<uint4*>(&gtile[r][v * 4]) = val;
     }
     __syncthreads();
-    load_tile(tile, u, b, T, d, t0, c0);
-    __syncthreads();
-    // dweight[c][k] += sum_t dw[t] * u[t + k - 15]
+    // u row for (t, tap) is t + tap (the tile starts at t0 - 15)
+    float2 win[4];
 #pragma unroll
-    for (int j = 0; j < OPT + KW - 1; ++j) {
-      const float2 v = __bfloat1622float2(tile[strip * OPT + j][lane]);
+    for (int k = 0; k < 3; ++k) win[k + 1] = __bfloat1622float2(utile[tap0 + k][lane]);
+#pragma unroll 8
+    for (int t = 0; t < TT; ++t) {
+      win[0] = win[1]; win[1] = win[2]; win[2] = win[3];
+      const int r = min(t + tap0 + 3, ROWS - 1);
+      win[3] = __bfloat1622float2(utile[r][lane]);
+      const float2 g = __bfloat1622float2(gtile[t][lane]);
 #pragma unroll
-      for (int o = 0; o < OPT; ++o) {
-        const int k = j - o;
-        if (k >= 0 && k < KW) {
-          wacc[k].x = fmaf(g[o].x, v.x, wacc[k].x);
-          wacc[k].y = fmaf(g[o].y, v.y, wacc[k].y);
-        }
+      for (int k = 0; k < 4; ++k) {
+        acc[k].x = fmaf(g.x, win[k].x, acc[k].x);
+        acc[k].y = fmaf(g.y, win[k].y, acc[k].y);
       }
+      if (w == 7) { gsum.x += g.x; gsum.y += g.y; }
     }
   }
 #pragma unroll
-  for (int k = 0; k < KW; ++k) {
-    atomicAdd(&red[2 * lane][k], wacc[k].x);
-    atomicAdd(&red[2 * lane + 1][k], wacc[k].y);
+  for (int k = 0; k < 4; ++k) {
+    const int tap = tap0 + k;
+    if (tap < KW) {
+      atomicAdd(dweight + (long long)ch * KW + tap, acc[k].x);
+      atomicAdd(dweight + (long long)(ch + 1) * KW + tap, acc[k].y);
+    }
   }
-  atomicAdd(&red[2 * lane][KW], gsum.x);
-  atomicAdd(&red[2 * lane + 1][KW], gsum.y);
-  __syncthreads();
-  for (int i = threadIdx.x; i < CC * (KW + 1); i += DW_THREADS) {
-    const int c = i / (KW + 1), k = i - c * (KW + 1);
-    const float v = red[c][k];
-    if (k < KW) atomicAdd(dweight + (long long)(c0 + c) * KW + k, v);
-    else if (dbias != nullptr) atomicAdd(dbias + c0 + c, v);
+  if (w == 7 && dbias != nullptr) {
+    atomicAdd(dbias + ch, gsum.x);
+    atomicAdd(dbias + ch + 1, gsum.y);
   }
 }
 
@@ -197,14 +207,18 @@ extern "C" int tasr_dwconv31_bwd(const void* dw, const void* u, const void* ab, 
                                  const float* weight, void* dab, void* du, float* dweight, float* dbias,
                                  tasr_stream_t stream) {
   if (d % CC || B <= 0 || T <= 0) return TASR_ERR_SHAPE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int ntiles = cdiv(T, TT);
-  int nseg = 444 / max(1, B * (d / CC));  // enough CTAs for ~3 per SM, otherwise as few segments as possible
+  dim3 grid_a(d / CC, ntiles, B);
+  dwconv_bwd_data_kernel<<<grid_a, DW_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dw), reinterpret_cast<const bf16*>(ab), T, d,
+                                                        weight, reinterpret_cast<bf16*>(dab), reinterpret_cast<bf16*>(du));
+  TASR_CHECK_LAUNCH();
+  int nseg = 592 / max(1, B * (d / CC));  // ~4 CTAs per SM, otherwise as few segments (= atomics) as possible
   nseg = max(1, min(nseg, ntiles));
   const int tiles_per_cta = cdiv(ntiles, nseg);
-  dim3 grid(d / CC, cdiv(ntiles, tiles_per_cta), B);
-  dwconv_bwd_kernel<<<grid, DW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(dw), reinterpret_cast<const bf16*>(u), reinterpret_cast<const bf16*>(ab), T, d,
-      weight, reinterpret_cast<bf16*>(dab), reinterpret_cast<bf16*>(du), dweight, dbias, tiles_per_cta);
+  dim3 grid_b(d / CC, cdiv(ntiles, tiles_per_cta), B);
+  dwconv_bwd_weight_kernel<<<grid_b, DW_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dw), reinterpret_cast<const bf16*>(u), T, d,
+                                                          dweight, dbias, tiles_per_cta);
   TASR_CHECK_LAUNCH();
   return TASR_OK;
 }
