@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(NT) conv1_fwd_kernel(const float* __restrict__
   const int c0 = (threadIdx.x % lanes_per_item) << 3;
   const int sub = threadIdx.x / lanes_per_item;
   const long long total = (long long)B * T1 * F1;
+#pragma unroll 2
   for (long long pix = (long long)blockIdx.x * items_per_iter + sub; pix < total; pix += (long long)gridDim.x * items_per_iter) {
     const int w = (int)(pix % F1);
     const long long bh = pix / F1;
@@ -516,7 +517,7 @@ extern "C" int tasr_conv1_fwd(const float* x, int B, int T, int F, int d, const 
   Geom g = geom(T, F);
   const long long total = (long long)B * g.T1 * g.F1;
   const int per = NT / (d / 8);
-  const int grid = (int)imin64((long long)148 * 8, (total + per - 1) / per);
+  const int grid = (int)imin64((long long)148 * 16, (total + per - 1) / per);
   conv1_fwd_kernel<<<grid, NT, (size_t)10 * d * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       x, B, T, F, d, w1, b1, g.T1, g.F1, reinterpret_cast<bf16*>(y1));
   TASR_CHECK_LAUNCH();
@@ -529,7 +530,7 @@ extern "C" int tasr_conv1_bwd(const void* dy1, const float* x, int B, int T, int
   Geom g = geom(T, F);
   const long long total = (long long)B * g.T1 * g.F1;
   const int per = NT / (d / 8);
-  const int grid = (int)imin64((long long)148 * 4, (total + per - 1) / per);
+  const int grid = (int)imin64((long long)148 * 6, (total + per - 1) / per);
   conv1_bwd_kernel<<<grid, NT, (size_t)20 * d * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(dy1), x, B, T, F, d, w1, b1, g.T1, g.F1, dw1, db1);
   TASR_CHECK_LAUNCH();

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(NT) gn_stats_kernel(const float* __restrict__ 
   const int rl = threadIdx.x / tpr;
   const int t0 = chunk * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
   float s = 0.f, ss = 0.f;
+#pragma unroll 4
   for (int t = t0 + rl; t < t1; t += rlanes) {
     float4 v = ld4(x + ((long long)b * T + t) * d + col);
     s += (v.x + v.y) + (v.z + v.w);
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const float* __restrict__ 
   const float mean = sh_mean[g], rstd = sh_rstd[g];
   const float4 ga = ld4(gamma + col), be = ld4(beta + col);
   const int t0 = blockIdx.x * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
+#pragma unroll 4
   for (int t = t0 + rl; t < t1; t += rlanes) {
     const long long off = ((long long)b * T + t) * d + col;
     float4 v = ld4(x + off);
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_stats_kernel(const void* __restrict
   const float mean = stats[((long long)b * G + g) * 2], rstd = stats[((long long)b * G + g) * 2 + 1];
   const int t0 = chunk * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
   float4 a = make_float4(0, 0, 0, 0), c = make_float4(0, 0, 0, 0);
+#pragma unroll 4
   for (int t = t0 + rl; t < t1; t += rlanes) {
     const long long off = ((long long)b * T + t) * d + col;
     float4 xv = ld4(x + off);
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const void* __restrict
   const float s1 = sh_s1[g], s2 = sh_s2[g];
   const float4 ga = ld4(gamma + col);
   const int t0 = blockIdx.x * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
+#pragma unroll 4
   for (int t = t0 + rl; t < t1; t += rlanes) {
     const long long off = ((long long)b * T + t) * d + col;
     float4 xv = ld4(x + off);
@@ -350,7 +354,7 @@ bool gn_shape_ok(int d, int G) {
   return tpr <= NT && (NT % tpr) == 0;
 }
 int gn_rows_per_cta(int B, int T) {
-  int chunks = max(1, 296 / max(B, 1));
+  int chunks = max(1, 1184 / max(B, 1));  // ~8 CTAs (of 8 warps) per SM: these kernels are latency bound otherwise
   int rows = cdiv(T, chunks);
   return max(rows, 8);
 }
