@@ -308,6 +308,42 @@ __device__ __forceinline__ void conv1_point(const float* __restrict__ xb, int T,
   }
 }
 
+// Each thread: 8 channels x PX = 4 neighbouring output columns of one row (the 3 x 9 input patch and the 72
+// weights are loaded once for 32 outputs).
+constexpr int PX = 4;
+
+__device__ __forceinline__ void load_patch(const float* __restrict__ xb, int T, int F, int h, int w0, float (*xp)[2 * PX + 1]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int tt = 2 * h - 1 + i;
+    const bool rok = tt >= 0 && tt < T;
+#pragma unroll
+    for (int j = 0; j < 2 * PX + 1; ++j) {
+      const int ff = 2 * w0 - 1 + j;
+      xp[i][j] = (rok && ff >= 0 && ff < F) ? xb[(long long)tt * F + ff] : 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void conv1_rows(const float (*xp)[2 * PX + 1], const float* __restrict__ w1s,
+                                           const float* __restrict__ b1s, int d, int c0, float (*z)[8]) {
+#pragma unroll
+  for (int px = 0; px < PX; ++px)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) z[px][q] = b1s[c0 + q];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float4 wa = *reinterpret_cast<const float4*>(w1s + k * d + c0);
+    const float4 wb = *reinterpret_cast<const float4*>(w1s + k * d + c0 + 4);
+    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+    for (int px = 0; px < PX; ++px) {
+      const float xv = xp[k / 3][2 * px + k % 3];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) z[px][q] = fmaf(xv, wv[q], z[px][q]);
+    }
+  }
+}
+
 // x (B, T, F) fp32 -> y1 (B, T1, F1, d) bf16 = silu(conv1(x))
 __global__ void __launch_bounds__(NT) conv1_fwd_kernel(const float* __restrict__ x, int B, int T, int F, int d,
                                                        const float* __restrict__ w1, const float* __restrict__ b1, int T1,
@@ -325,20 +361,27 @@ __global__ void __launch_bounds__(NT) conv1_fwd_kernel(const float* __restrict__
   const int items_per_iter = NT / lanes_per_item;
   const int c0 = (threadIdx.x % lanes_per_item) << 3;
   const int sub = threadIdx.x / lanes_per_item;
-  const long long total = (long long)B * T1 * F1;
-#pragma unroll 2
-  for (long long pix = (long long)blockIdx.x * items_per_iter + sub; pix < total; pix += (long long)gridDim.x * items_per_iter) {
-    const int w = (int)(pix % F1);
-    const long long bh = pix / F1;
+  const int wgroups = (F1 + PX - 1) / PX;
+  const long long total = (long long)B * T1 * wgroups;
+  for (long long item = (long long)blockIdx.x * items_per_iter + sub; item < total; item += (long long)gridDim.x * items_per_iter) {
+    const int wg = (int)(item % wgroups);
+    const long long bh = item / wgroups;
     const int h = (int)(bh % T1), b = (int)(bh / T1);
-    float z[8], xin[9];
-    conv1_point(x + (long long)b * T * F, T, F, h, w, w1s, b1s, d, c0, z, xin);
-    uint4 o;
-    o.x = pack_bf16x2(siluf_(z[0]), siluf_(z[1]));
-    o.y = pack_bf16x2(siluf_(z[2]), siluf_(z[3]));
-    o.z = pack_bf16x2(siluf_(z[4]), siluf_(z[5]));
-    o.w = pack_bf16x2(siluf_(z[6]), siluf_(z[7]));
-    *reinterpret_cast<uint4*>(y1 + pix * d + c0) = o;
+    const int w0 = wg * PX;
+    float xp[3][2 * PX + 1], z[PX][8];
+    load_patch(x + (long long)b * T * F, T, F, h, w0, xp);
+    conv1_rows(xp, w1s, b1s, d, c0, z);
+#pragma unroll
+    for (int px = 0; px < PX; ++px) {
+      if (w0 + px < F1) {
+        uint4 o;
+        o.x = pack_bf16x2(siluf_(z[px][0]), siluf_(z[px][1]));
+        o.y = pack_bf16x2(siluf_(z[px][2]), siluf_(z[px][3]));
+        o.z = pack_bf16x2(siluf_(z[px][4]), siluf_(z[px][5]));
+        o.w = pack_bf16x2(siluf_(z[px][6]), siluf_(z[px][7]));
+        *reinterpret_cast<uint4*>(y1 + (((long long)b * T1 + h) * F1 + w0 + px) * d + c0) = o;
+      }
+    }
   }
 }
 
@@ -370,26 +413,36 @@ __global__ void __launch_bounds__(NT) conv1_bwd_kernel(const bf16* __restrict__ 
 #pragma unroll
     for (int k = 0; k < 9; ++k) gw[k][q] = 0.f;
   }
-  const long long total = (long long)B * T1 * F1;
-  for (long long pix = (long long)blockIdx.x * items_per_iter + sub; pix < total; pix += (long long)gridDim.x * items_per_iter) {
-    const int w = (int)(pix % F1);
-    const long long bh = pix / F1;
+  const int wgroups = (F1 + PX - 1) / PX;
+  const long long total = (long long)B * T1 * wgroups;
+  for (long long item = (long long)blockIdx.x * items_per_iter + sub; item < total; item += (long long)gridDim.x * items_per_iter) {
+    const int wg = (int)(item % wgroups);
+    const long long bh = item / wgroups;
     const int h = (int)(bh % T1), b = (int)(bh / T1);
-    const uint4 u = *reinterpret_cast<const uint4*>(dy1 + pix * d + c0);
-    float g[8];
-    float2 t;
-    t = unpack_bf16x2(u.x); g[0] = t.x; g[1] = t.y;
-    t = unpack_bf16x2(u.y); g[2] = t.x; g[3] = t.y;
-    t = unpack_bf16x2(u.z); g[4] = t.x; g[5] = t.y;
-    t = unpack_bf16x2(u.w); g[6] = t.x; g[7] = t.y;
-    float z[8], xin[9];
-    conv1_point(x + (long long)b * T * F, T, F, h, w, w1s, b1s, d, c0, z, xin);
+    const int w0 = wg * PX;
+    uint4 u[PX];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float dz = g[q] * silu_gradf_(z[q]);
-      gb[q] += dz;
+    for (int px = 0; px < PX; ++px)
+      u[px] = (w0 + px < F1) ? *reinterpret_cast<const uint4*>(dy1 + (((long long)b * T1 + h) * F1 + w0 + px) * d + c0)
+                             : make_uint4(0, 0, 0, 0);
+    float xp[3][2 * PX + 1], z[PX][8];
+    load_patch(x + (long long)b * T * F, T, F, h, w0, xp);
+    conv1_rows(xp, w1s, b1s, d, c0, z);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) gw[k][q] = fmaf(dz, xin[k], gw[k][q]);
+    for (int px = 0; px < PX; ++px) {
+      float g[8];
+      float2 t;
+      t = unpack_bf16x2(u[px].x); g[0] = t.x; g[1] = t.y;
+      t = unpack_bf16x2(u[px].y); g[2] = t.x; g[3] = t.y;
+      t = unpack_bf16x2(u[px].z); g[4] = t.x; g[5] = t.y;
+      t = unpack_bf16x2(u[px].w); g[6] = t.x; g[7] = t.y;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float dz = g[q] * silu_gradf_(z[px][q]);
+        gb[q] += dz;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) gw[k][q] = fmaf(dz, xp[k / 3][2 * px + k % 3], gw[k][q]);
+      }
     }
   }
 #pragma unroll
@@ -515,9 +568,9 @@ extern "C" int tasr_conv1_fwd(const float* x, int B, int T, int F, int d, const 
                               tasr_stream_t stream) {
   if (d % 8 || d > 2048 || (NT % (d / 8)) || B <= 0 || T <= 0 || F <= 0) return TASR_ERR_SHAPE;
   Geom g = geom(T, F);
-  const long long total = (long long)B * g.T1 * g.F1;
+  const long long total = (long long)B * g.T1 * ((g.F1 + PX - 1) / PX);
   const int per = NT / (d / 8);
-  const int grid = (int)imin64((long long)148 * 16, (total + per - 1) / per);
+  const int grid = (int)imin64((long long)148 * 8, (total + per - 1) / per);
   conv1_fwd_kernel<<<grid, NT, (size_t)10 * d * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       x, B, T, F, d, w1, b1, g.T1, g.F1, reinterpret_cast<bf16*>(y1));
   TASR_CHECK_LAUNCH();
@@ -528,9 +581,9 @@ extern "C" int tasr_conv1_bwd(const void* dy1, const float* x, int B, int T, int
                               float* dw1, float* db1, tasr_stream_t stream) {
   if (d % 8 || d > 1024 || (NT % (d / 8)) || B <= 0 || T <= 0 || F <= 0) return TASR_ERR_SHAPE;
   Geom g = geom(T, F);
-  const long long total = (long long)B * g.T1 * g.F1;
+  const long long total = (long long)B * g.T1 * ((g.F1 + PX - 1) / PX);
   const int per = NT / (d / 8);
-  const int grid = (int)imin64((long long)148 * 6, (total + per - 1) / per);
+  const int grid = (int)imin64((long long)148 * 4, (total + per - 1) / per);
   conv1_bwd_kernel<<<grid, NT, (size_t)20 * d * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(dy1), x, B, T, F, d, w1, b1, g.T1, g.F1, dw1, db1);
   TASR_CHECK_LAUNCH();
