@@ -101,3 +101,57 @@ def test_backward_parity(cuda):
     bad = {k: v for k, v in worst.items() if v > 6e-2}
     assert not bad, bad
     assert np.median(list(worst.values())) < 2e-2
+
+
+def test_conformer_m_scale_parity(cuda):
+    """BASELINE configs[2] shape family: d_model 512, 8 heads (GroupNorm 32 groups x 16 channels), 2 blocks."""
+    model, sd, x, il = _make(cuda, d=512, H=8, nb=2, V=1000, B=2, T=171, seed=3)
+    ref = oc.forward(x, il, sd, 8, 2, training=True)
+    out = model(x.to(cuda), il)
+    assert out.shape == ref.shape
+    assert _rel(out, ref) < 2e-2
+    g = torch.Generator().manual_seed(9)
+    targets = torch.randint(1, 1000, (2, 8), generator=g)
+    tl = torch.tensor([8, 5])
+    pnames = {n for n, _ in model.named_parameters()}
+    sdr = {k: (v.clone().requires_grad_(True) if k in pnames else v) for k, v in sd.items()}
+    loss_ref = oc.ctc_loss_torch(oc.forward(x, il, sdr, 8, 2, training=True), targets, il, tl)
+    loss_ref.backward()
+    loss, _, dlogits = L.ctc_loss_fwd_bwd(out.detach(), targets.to(cuda), (il // 4).to(cuda), tl.to(cuda))
+    out.backward(dlogits)
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    rels = []
+    for name, p in model.named_parameters():
+        gref = sdr[name].grad
+        if gref is None or name.endswith("depthwise_conv.bias"):
+            continue
+        rels.append(_rel(p.grad, gref))
+    assert max(rels) < 8e-2 and np.median(rels) < 2e-2
+
+
+def test_long_form_inference_and_greedy_decode(cuda):
+    """BASELINE configs[3] shape family: 60 s utterances (T = 6001 mel frames -> T' = 1501), eval mode, padding
+    mask, greedy CTC decode; logits vs the oracle, token ids bit-exact on identical logits."""
+    from turkish_asr_model_b200.utils.decoding import GreedyDecoder
+    torch.manual_seed(4)
+    model = TurkishASRModel(80, 256, 4, 2, 200, dropout=0.1)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(cuda).eval()
+    g = torch.Generator().manual_seed(5)
+    T = 6001
+    x = torch.randn(2, T, 80, generator=g)
+    il = torch.tensor([6001, 4321])
+    x[1, 4321:] = 0
+    with torch.no_grad():
+        out = model(x.to(cuda), il)
+    ref = oc.forward(x, il, sd, 4, 2, training=False)
+    assert out.shape == ref.shape == (2, 1501, 200)
+    assert oc.encoder_frames(T) == 1501 and int(il[0]) // 4 == 1500  # L' = T // 4 <= T' (SURVEY finding 5)
+    assert _rel(out, ref) < 2e-2
+    lengths = il // 4
+    ids_ref, toks_ref = oc.greedy_ids(out.float().cpu(), lengths)
+    toks = GreedyDecoder(None, blank_id=0).decode_ids_batch(out, lengths)
+    assert toks == toks_ref
+    with torch.no_grad():  # no mask at all (reference inference path, inference.py:117)
+        out2 = model(x.to(cuda), None)
+    assert _rel(out2, oc.forward(x, None, sd, 4, 2, training=False)) < 2e-2
