@@ -155,3 +155,45 @@ def test_long_form_inference_and_greedy_decode(cuda):
     with torch.no_grad():  # no mask at all (reference inference path, inference.py:117)
         out2 = model(x.to(cuda), None)
     assert _rel(out2, oc.forward(x, None, sd, 4, 2, training=False)) < 2e-2
+
+
+def test_standalone_submodules_match_oracle(cuda):
+    """ConformerBlock / sub-modules called on their own (reference API, model/conformer.py:90-135) with autograd."""
+    from turkish_asr_model_b200.model import ConformerBlock
+    torch.manual_seed(1)
+    blk = ConformerBlock(256, 4, dropout=0.0)
+    sd = {"b." + k: v.detach().clone() for k, v in blk.state_dict().items()}
+    blk = blk.to(cuda).train()
+    g = torch.Generator().manual_seed(2)
+    B, T = 2, 90
+    x = torch.randn(B, T, 256, generator=g)
+    lens = torch.tensor([90, 51])
+    mask = (torch.arange(T)[None, :] < lens[:, None])[:, None, None, :]
+    pnames = {"b." + n for n, _ in blk.named_parameters()}
+    sdr = {k: (v.clone().requires_grad_(True) if k in pnames else v) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    ref = oc.block(xr, sdr, "b.", 4, lens, training=True)
+    dy = torch.randn(B, T, 256, generator=g)
+    ref.backward(dy)
+    xd = x.to(cuda).requires_grad_(True)
+    out = blk(xd, mask=mask.to(cuda))
+    assert _rel(out, ref.detach()) < 2e-2
+    out.backward(dy.to(cuda))
+    assert _rel(xd.grad, xr.grad) < 5e-2
+    rels = []
+    for name, p in blk.named_parameters():
+        gref = sdr["b." + name].grad
+        if gref is None:
+            assert p.grad is None
+            continue
+        if name.endswith("depthwise_conv.bias"):
+            continue
+        rels.append(_rel(p.grad, gref))
+    assert max(rels) < 8e-2 and np.median(rels) < 2e-2
+    # individual modules
+    y = blk.ff1(xd.detach())
+    assert _rel(y, oc.swiglu_ff(x, sd, "b.ff1.")) < 2e-2
+    a, w = blk.attn(xd.detach(), xd.detach(), xd.detach(), mask=mask.to(cuda))
+    assert w is None and _rel(a, oc.mqa_attention(x, sd, "b.attn.", 4, lens)) < 2e-2
+    n = blk.norm_ff1(xd.detach())
+    assert _rel(n, oc.group_norm_tokens(x, sd["b.norm_ff1.norm.weight"], sd["b.norm_ff1.norm.bias"])) < 1e-4

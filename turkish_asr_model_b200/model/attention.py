@@ -48,4 +48,7 @@ class RelativeMultiHeadAttention(nn.Module):
 
     def forward(self, x, x_k=None, x_v=None, mask=None):
         from ..functional import attention_module_forward
+        for other in (x_k, x_v):
+            if other is not None and other is not x and not (other.data_ptr() == x.data_ptr() and other.shape == x.shape):
+                raise NotImplementedError("self-attention only (the reference always passes the same tensor three times)")
         return attention_module_forward(self, x, mask), None
