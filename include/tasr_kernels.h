@@ -232,6 +232,19 @@ int tasr_conv2_dgrad(const void* dz2, int B, int T, int F, int d, const void* w2
 int tasr_conv2_wgrad(const void* dz2, const void* y1, int B, int T, int F, int d, float* dw2, tasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Augmentation (BASELINE configs[4]).
+ *   resample_sinc: torchaudio.functional.resample(lowpass_filter_width=6, rolloff=0.99, sinc_interp_hann)
+ *     as used by data/preprocessing.py:191-228 SpeedPerturbation; per utterance orig/new frequency ALREADY
+ *     divided by their gcd; out length ceil(new*N/orig); y (B, y_ld) is zero beyond it up to max_out.
+ *   specaugment: data/preprocessing.py:132-188; params (B, nmask, 3) int32 = (axis 0 freq | 1 time, start, end)
+ *     drawn on the host like torchaudio's mask_along_axis; positions [start, end) are set to 0.0 in place.
+ * ---------------------------------------------------------------------------------------------- */
+int tasr_resample_sinc(const float* x, int64_t x_ld, const int32_t* n_in, const int32_t* orig_freq,
+                       const int32_t* new_freq, int B, float* y, int64_t y_ld, int max_out, tasr_stream_t stream);
+int tasr_specaugment(float* feats, int B, int T, int F, const int32_t* params, int nmask, const int64_t* frames,
+                     tasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused log-softmax + CTC loss (mean reduction, zero_infinity) + gradient w.r.t. the logits.
  * Replaces: trainer/trainer.py:167-173 (log_softmax + nn.CTCLoss(blank=0, zero_infinity=True)) and
  *   their backward.  logits (B,T,V) bf16 or fp32 with row pitch ld >= V elements (dlogits: same pitch); targets (B,Smax) int64 padded; lengths int64 (B),

@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 1200 python -m pytest tests/test_model_gpu.py -q -m gpu --timeout 600 -x -k "standalone" > gpurun_out/test.log 2>&1
+timeout -s KILL 1200 python -m pytest tests/test_augment.py -q -m gpu --timeout 600 -x > gpurun_out/test.log 2>&1
 echo "exit $?" >> gpurun_out/test.log
 tail -40 gpurun_out/test.log

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "tasr_conv2_fwd": (I, [P, I, I, I, I, P, P, P, P, P]),
     "tasr_conv2_dgrad": (I, [P, I, I, I, I, P, P, P]),
     "tasr_conv2_wgrad": (I, [P, P, I, I, I, I, P, P]),
+    "tasr_resample_sinc": (I, [P, L, P, P, P, I, P, L, I, P]),
+    "tasr_specaugment": (I, [P, I, I, I, P, I, P, P]),
     "tasr_ctc_workspace_bytes": (Z, [I, I, I, I]),
     "tasr_ctc_loss_fwd_bwd": (I, [P, I, L, I, I, I, P, I, P, P, I, F, P, P, P, P, Z, P]),
     "tasr_grad_sumsq": (I, [P, L, P, P]),
@@ -443,3 +445,24 @@ def gemm_replay(profile):
     sp = stream_ptr()
     for _, a, _, _ in profile:
         check(fn(C.addressof(a), sp))
+
+
+# ---------------------------------------------------------------------------------------------
+# augmentation
+# ---------------------------------------------------------------------------------------------
+def resample_sinc(waves, n_in, orig, new, max_out):
+    """waves (B, Nmax) fp32; n_in/orig/new (B,) int32 (frequencies divided by their gcd) -> (B, max_out) fp32."""
+    require_cuda(waves, n_in, orig, new)
+    B = waves.shape[0]
+    y = torch.empty(B, max_out, dtype=torch.float32, device=waves.device)
+    check(lib().tasr_resample_sinc(ptr(waves), waves.stride(0), ptr(n_in), ptr(orig), ptr(new), B, ptr(y), y.stride(0),
+                                   max_out, stream_ptr()))
+    return y
+
+
+def specaugment_(feats, params, frames=None):
+    """feats (B,T,F) fp32 in place; params (B, nmask, 3) int32 cuda."""
+    require_cuda(feats, params)
+    B, T, F = feats.shape
+    check(lib().tasr_specaugment(ptr(feats), B, T, F, ptr(params), params.shape[1], ptr(frames), stream_ptr()))
+    return feats

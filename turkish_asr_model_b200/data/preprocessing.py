@@ -135,3 +135,64 @@ class SpecAugment:
             else:
                 out[max(s, 0):e, :] = 0.0
         return out
+
+
+    def apply_batch(self, feats: torch.Tensor, frames: torch.Tensor, params=None) -> torch.Tensor:
+        """Batched GPU form: feats (B, Tmax, n_mels) CUDA, masked in place; per-utterance parameters are drawn on the
+        host exactly as the reference would draw them utterance by utterance (size = that utterance's frame count)."""
+        B, T, F = feats.shape
+        frames_cpu = frames.cpu().tolist()
+        if params is None:
+            params = [self.mask_params(int(n), F) for n in frames_cpu]
+        flat = [[(0 if a == "f" else 1), int(s), int(e)] for per in params for (a, s, e) in per]
+        nmask = len(params[0]) if params else 0
+        p = torch.tensor(flat, dtype=torch.int32).view(B, nmask, 3).to(feats.device)
+        L.specaugment_(feats, p, frames.to(device=feats.device, dtype=torch.int64))
+        return feats
+
+
+class SpeedPerturbation:
+    """reference data/preprocessing.py:191-228: pick speed in `speeds` with torch.randint, resample with
+    torchaudio.functional.resample(waveform, sr, int(sr / speed)).  The resampling runs on the GPU
+    (tasr_resample_sinc evaluates the <= 15 non-zero windowed-sinc taps per output sample on the fly)."""
+
+    def __init__(self, speeds=(0.9, 1.0, 1.1)):
+        self.speeds = list(speeds)
+
+    def pick(self):
+        return self.speeds[int(torch.randint(len(self.speeds), (1,)).item())]
+
+    @staticmethod
+    def freqs(speed: float, sample_rate: int):
+        import math
+        new_freq = int(sample_rate / speed)
+        g = math.gcd(sample_rate, new_freq)
+        return sample_rate // g, new_freq // g
+
+    def apply_batch(self, waves: torch.Tensor, n_samples: torch.Tensor, sample_rate: int = TARGET_SAMPLE_RATE, speeds=None):
+        """waves (B, Nmax) CUDA, n_samples (B,) -> (resampled (B, Nmax'), new lengths (B,) int64 = ceil(new*N/orig))."""
+        B = waves.shape[0]
+        if speeds is None:
+            speeds = [self.pick() for _ in range(B)]
+        ns = n_samples.cpu().tolist()
+        orig, new, out_len = [], [], []
+        for n, sp in zip(ns, speeds):
+            o, m = (1, 1) if sp == 1.0 else self.freqs(sp, sample_rate)
+            orig.append(o)
+            new.append(m)
+            out_len.append(-(-m * int(n) // o))
+        dev = waves.device if waves.is_cuda else torch.device("cuda")
+        y = L.resample_sinc(waves.to(dev).contiguous().float(), torch.tensor(ns, dtype=torch.int32, device=dev),
+                            torch.tensor(orig, dtype=torch.int32, device=dev), torch.tensor(new, dtype=torch.int32, device=dev),
+                            max(out_len))
+        return y, torch.tensor(out_len, dtype=torch.int64)
+
+    def __call__(self, waveform: torch.Tensor, sample_rate: int):
+        """Reference call signature: (1, N) or (N,) waveform -> (perturbed waveform, sample_rate)."""
+        speed = self.pick()
+        if speed == 1.0:
+            return waveform, sample_rate
+        w = waveform.reshape(1, -1)
+        y, n = self.apply_batch(w, torch.tensor([w.shape[1]]), sample_rate, speeds=[speed])
+        y = y[:, : int(n[0])].to(waveform.device)
+        return (y if waveform.dim() == 2 else y[0]), sample_rate
