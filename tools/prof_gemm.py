@@ -25,6 +25,15 @@ def plain(): L.gemm(M, 2 * dff, d, x, d, W1, d, L.EPI_STORE, gv, 2 * dff, bias=b
 fns = {"ff1": ff1, "ff2": ff2, "ff2_dgrad": ff2_dgrad, "ff1_wgrad": ff1_wgrad, "ff1_dgrad": ff1_dgrad, "plain": plain}
 flops = {"ff1": 2 * M * 2 * dff * d, "ff2": 2 * M * d * dff, "ff2_dgrad": 2 * M * dff * d, "ff1_wgrad": 2 * M * 2 * dff * d,
          "ff1_dgrad": 2 * M * 2 * dff * d, "plain": 2 * M * 2 * dff * d}
+if which == "once":  # one warm-up + one measured launch per shape (for ncu --set full)
+    for name, fn in fns.items():
+        fn()
+    torch.cuda.synchronize()
+    for name, fn in fns.items():
+        fn()
+    torch.cuda.synchronize()
+    print("once done")
+    sys.exit(0)
 for name, fn in fns.items():
     if which != "all" and which != name:
         continue

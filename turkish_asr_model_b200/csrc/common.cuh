@@ -89,6 +89,21 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned
   const uint32_t lane = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
   return lane >= thresh16 ? inv_keep : 0.f;
 }
+// fast path for a run of pairs that does not cross a 2^32 boundary: `base32` = lo32(pair0) + lo32(seed) +
+// hi32(pair0) * 0x9E3779B1 is computed once, pair j of the run costs one add + the mixer
+__host__ __device__ __forceinline__ uint32_t tasr_hash_pair_base(unsigned long long seed, unsigned long long pair0) {
+  return (uint32_t)pair0 + (uint32_t)seed + (uint32_t)(pair0 >> 32) * 0x9E3779B1u;
+}
+__device__ __forceinline__ void dropout_scale2_fast(uint32_t base32, uint32_t seed_hi, uint32_t j, uint32_t thresh16,
+                                                    float inv_keep, float& s0, float& s1) {
+  uint32_t x = base32 + j;
+  x ^= x >> 16; x *= 0x7FEB352Du;
+  x ^= seed_hi;
+  x ^= x >> 15; x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  s0 = (x & 0xFFFFu) >= thresh16 ? inv_keep : 0.f;
+  s1 = (x >> 16) >= thresh16 ? inv_keep : 0.f;
+}
 // both elements of the pair (idx even, idx + 1) with one hash
 __device__ __forceinline__ void dropout_scale2(unsigned long long seed, unsigned long long idx_even, uint32_t thresh16,
                                                float inv_keep, float& s0, float& s1) {
@@ -131,6 +146,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+// same, yielding the issue slots between polls (producer / MMA warps share their SM sub-partitions with epilogue warps)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
 }
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -86,7 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_wait_backoff(&empty_bar[s], ph ^ 1u);
           mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
           const int k0 = kb * BK;
           uint8_t* a_dst = sA + s * A_BYTES;
@@ -115,7 +115,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
         const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
-        mbar_wait(&tempty_bar[acc], aph ^ 1u);  // epilogue has drained this accumulator
+        mbar_wait_backoff(&tempty_bar[acc], aph ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
@@ -404,7 +404,7 @@ int fill_dev(const tasr_gemm_args* a, GemmDev* p, bool* dual) {
   p->alpha = a->alpha; p->n_half = a->n_half;
   p->drop_thresh = tasr_drop_thresh16(a->drop_p);
   p->drop_inv_keep = tasr_drop_inv_keep(p->drop_thresh);
-  if (p->drop_thresh && (a->N & 1)) return TASR_ERR_SHAPE;  // the pair-hash dropout mask needs an even row length
+  if (p->drop_thresh && (a->N & 31)) return TASR_ERR_SHAPE;  // the pair-hash dropout mask is generated in runs of 32 columns
   p->seed = a->seed;
   p->seed_ptr = g_tasr_seed_ptr;
   p->remap_p0 = a->remap_p0; p->remap_p1 = a->remap_p1;

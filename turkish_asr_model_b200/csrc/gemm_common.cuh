@@ -79,54 +79,76 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // The mode is a template parameter: only that mode's code is generated (the step is epilogue-bound for
 // the K = 256 GEMMs, and one 32-column chunk of a generic switch was ~15k SASS instructions).
 // ------------------------------------------------------------------------------------------------
+// bias for 32 consecutive columns (vectorised when the chunk is full and aligned)
+__device__ __forceinline__ void load_bias32(const float* __restrict__ bias, int col0, int nvalid, float* b) {
+  if (bias == nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = 0.f;
+  } else if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
+    const float4* s4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 f = __ldg(s4 + i);
+      b[4 * i] = f.x; b[4 * i + 1] = f.y; b[4 * i + 2] = f.z; b[4 * i + 3] = f.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = (i < nvalid) ? bias[col0 + i] : 0.f;
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col0, float* lo, float* hi, float* t3) {
   const int nvalid = (row < p.M) ? max(0, min(32, p.N - col0)) : 0;
   const long long r = row;
-  const unsigned long long seed = (p.drop_thresh && p.seed_ptr) ? p.seed + *p.seed_ptr : p.seed;
-  const unsigned long long idx0 = (unsigned long long)(r * p.N + col0);  // even: N is even when dropout is on
+  // dropout: pair-hash over the run of 16 pairs of this chunk (N % 32 == 0 is checked on the host, so the run
+  // starts at a multiple of 16 pairs and cannot cross a 2^32 boundary)
+  uint32_t dbase = 0, dseed_hi = 0;
+  if (p.drop_thresh) {
+    const unsigned long long seed = p.seed_ptr ? p.seed + *p.seed_ptr : p.seed;
+    dbase = tasr_hash_pair_base(seed, (unsigned long long)(r * p.N + col0) >> 1);
+    dseed_hi = (uint32_t)(seed >> 32);
+  }
   if (EPI == TASR_EPI_STORE) {
+    load_bias32(p.bias, col0, nvalid, t3);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float b = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
-      lo[i] = p.alpha * (lo[i] + b);
-    }
+    for (int i = 0; i < 32; ++i) lo[i] = p.alpha * (lo[i] + t3[i]);
   } else if (EPI == TASR_EPI_RESID) {
+    float bb[32];
+    load_bias32(p.bias, col0, nvalid, bb);
     load_f32_chunk(reinterpret_cast<const float*>(p.aux) + r * p.ldaux + col0, t3, nvalid);
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const float b0 = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
-      const float b1 = (p.bias != nullptr && i + 1 < nvalid) ? p.bias[col0 + i + 1] : 0.f;
-      float v0 = lo[i] + b0, v1 = lo[i + 1] + b1;
+      float v0 = lo[i] + bb[i], v1 = lo[i + 1] + bb[i + 1];
       if (p.drop_thresh) {
         float s0, s1;
-        dropout_scale2(seed, idx0 + i, p.drop_thresh, p.drop_inv_keep, s0, s1);
+        dropout_scale2_fast(dbase, dseed_hi, i >> 1, p.drop_thresh, p.drop_inv_keep, s0, s1);
         v0 *= s0; v1 *= s1;
       }
       lo[i] = t3[i] + p.alpha * v0;
       lo[i + 1] = t3[i + 1] + p.alpha * v1;
     }
   } else if (EPI == TASR_EPI_SWIGLU || EPI == TASR_EPI_GLU) {
+    load_bias32(p.bias, col0, nvalid, t3);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) lo[i] = bf16_round(lo[i] + t3[i]);
+    load_bias32(p.bias ? p.bias + p.n_half : nullptr, col0, nvalid, t3);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) hi[i] = bf16_round(hi[i] + t3[i]);
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       float s0 = 1.f, s1 = 1.f;
-      if (p.drop_thresh) dropout_scale2(seed, idx0 + i, p.drop_thresh, p.drop_inv_keep, s0, s1);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int k = i + j;
-        const float b0 = (p.bias != nullptr && k < nvalid) ? p.bias[col0 + k] : 0.f;
-        const float b1 = (p.bias != nullptr && k < nvalid) ? p.bias[p.n_half + col0 + k] : 0.f;
-        lo[k] = bf16_round(lo[k] + b0);
-        hi[k] = bf16_round(hi[k] + b1);
-        const float v = (EPI == TASR_EPI_SWIGLU) ? siluf_(lo[k]) * hi[k] : lo[k] * sigmoidf_(hi[k]);
-        t3[k] = v * (j == 0 ? s0 : s1);
-      }
+      if (p.drop_thresh) dropout_scale2_fast(dbase, dseed_hi, i >> 1, p.drop_thresh, p.drop_inv_keep, s0, s1);
+      const float v0 = (EPI == TASR_EPI_SWIGLU) ? siluf_(lo[i]) * hi[i] : lo[i] * sigmoidf_(hi[i]);
+      const float v1 = (EPI == TASR_EPI_SWIGLU) ? siluf_(lo[i + 1]) * hi[i + 1] : lo[i + 1] * sigmoidf_(hi[i + 1]);
+      t3[i] = v0 * s0;
+      t3[i + 1] = v1 * s1;
     }
   } else if (EPI == TASR_EPI_SILU) {
+    load_bias32(p.bias, col0, nvalid, t3);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const float b = (p.bias != nullptr && i < nvalid) ? p.bias[col0 + i] : 0.f;
-      lo[i] = bf16_round(lo[i] + b);
+      lo[i] = bf16_round(lo[i] + t3[i]);
       t3[i] = siluf_(lo[i]);
     }
   } else if (EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) {
@@ -136,7 +158,7 @@ __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       float s0 = 1.f, s1 = 1.f;
-      if (p.drop_thresh) dropout_scale2(seed, idx0 + i, p.drop_thresh, p.drop_inv_keep, s0, s1);
+      if (p.drop_thresh) dropout_scale2_fast(dbase, dseed_hi, i >> 1, p.drop_thresh, p.drop_inv_keep, s0, s1);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int k = i + j;
