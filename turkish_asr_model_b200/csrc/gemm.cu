@@ -24,7 +24,7 @@ namespace {
 //   two epilogue groups of 4 warps each take alternate 64-column groups of a tile
 // ------------------------------------------------------------------------------------------------
 template <int EPI, int BN, int STAGES, int RINGG, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmDev p) {
   constexpr bool DUAL = (EPI == TASR_EPI_SWIGLU || EPI == TASR_EPI_GLU);
@@ -62,7 +62,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_THREADS);
+      mbar_init(&tempty_bar[a], G_EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -141,14 +141,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue: 2 groups x 4 warps =====================
-    const int ew = warp - 2;        // 0..7
-    const int grp = ew >> 2;        // epilogue group
-    const int q = warp & 3;         // TMEM lane quarter this warp may access
+    // ===================== epilogue: 2 super-groups x 8 warps =====================
+    // A super-group owns alternate 64-column groups of the tile; inside it, warp set `hsel` takes the 32-column
+    // half hsel of every group, 16 columns at a time (small register footprint -> 16 warps hide the latencies).
+    const int ew = warp - 2;          // 0..15
+    const int sg = ew >> 3;           // super-group
+    const int hsel = (ew >> 2) & 1;   // 32-column half inside a 64-column group
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int rloc = q * 32 + lane;
-    const bool leader = (q == ((2 + grp * 4) & 3)) && lane == 0;  // first warp of the group
-    const int bar_id = 1 + grp;
-    uint8_t* ring_base = sC + grp * RINGG * STAGE_BYTES;
+    const bool leader = ((ew & 7) == 0) && lane == 0;
+    const int bar_id = 1 + sg;
+    uint8_t* ring_base = sC + sg * RINGG * STAGE_BYTES;
     constexpr bool F32_MODE = (EPI == TASR_EPI_RESID || EPI == TASR_EPI_ATOMIC);
     const bool f32_out = F32_MODE || (EPI == TASR_EPI_STORE && p.out_f32);
     const bool direct_atomic = (EPI == TASR_EPI_ATOMIC) && (p.remap_p0 > 0);
@@ -164,24 +167,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t tbase = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int g = grp; g < TILE_N / 64; g += 2) {  // this group's 64-column groups
-        if (n0 + g * 64 >= p.N) break;               // fully out of range (uniform across the group)
+      for (int g = sg; g < TILE_N / 64; g += 2) {  // this super-group's 64-column groups
+        if (n0 + g * 64 >= p.N) break;              // fully out of range (uniform across the super-group)
         if (f32_out) {
           if (EPI == TASR_EPI_STORE || F32_MODE) {
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-              const int col0 = n0 + g * 64 + h * 32;
-              uint32_t lo_u[32];
-              tmem_ld32(tbase + g * 64 + h * 32, lo_u);
+            for (int u = 0; u < 2; ++u) {  // two 32-column fp32 staging buffers per group; this warp set: 16 of the 32
+              const int col0 = n0 + g * 64 + u * 32 + hsel * 16;
+              uint32_t lo_u[16];
+              tmem_ld16(tbase + g * 64 + u * 32 + hsel * 16, lo_u);
               tmem_ld_wait();
               float* lo = reinterpret_cast<float*>(lo_u);
-              float t3[32];
-              epilogue_math<EPI>(p, row, col0, lo, lo, t3);
+              float t3[16];
+              epilogue_math<EPI, 16>(p, row, col0, lo, lo, t3);
               if (direct_atomic) {
                 if (row < p.M) {
                   float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo;
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) {
+                  for (int i = 0; i < 16; ++i) {
                     int c = col0 + i;
                     if (c < p.N) {
                       c = (c % p.remap_p0) * p.remap_p1 + c / p.remap_p0;
@@ -192,14 +195,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 continue;
               }
               if (leader) bulk_wait_read<RINGG - 1>();
-              named_bar_sync(bar_id, EPI_GROUP_THREADS);
+              named_bar_sync(bar_id, G_SG_THREADS);
               uint8_t* buf = ring_base + (ring % RINGG) * STAGE_BYTES;
-              stage_f32(buf, rloc, lo);
+              stage_f32_16(buf, rloc, hsel * 4, lo);
               fence_proxy_async_smem();
-              named_bar_sync(bar_id, EPI_GROUP_THREADS);
+              named_bar_sync(bar_id, G_SG_THREADS);
               if (leader) {
-                if (EPI == TASR_EPI_ATOMIC) tma_reduce_add_2d(&tmO, buf, col0, m0);
-                else tma_store_2d(&tmO, buf, col0, m0);
+                const int c = n0 + g * 64 + u * 32;
+                if (EPI == TASR_EPI_ATOMIC) tma_reduce_add_2d(&tmO, buf, c, m0);
+                else tma_store_2d(&tmO, buf, c, m0);
                 bulk_commit();
               }
               ++ring;
@@ -208,37 +212,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else if (!F32_MODE) {
           // bf16 outputs: NBUF 64-column staging buffers per group
           if (leader) bulk_wait_read<RINGG - NBUF>();
-          named_bar_sync(bar_id, EPI_GROUP_THREADS);
+          named_bar_sync(bar_id, G_SG_THREADS);
           uint8_t* buf0 = ring_base + (ring % RINGG) * STAGE_BYTES;
           uint8_t* buf1 = ring_base + ((ring + 1) % RINGG) * STAGE_BYTES;
           uint8_t* buf2 = ring_base + ((ring + 2) % RINGG) * STAGE_BYTES;
 #pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            const int col0 = n0 + g * 64 + h * 32;
-            uint32_t lo_u[32], hi_u[32];
-            tmem_ld32(tbase + g * 64 + h * 32, lo_u);
-            if (DUAL) tmem_ld32(tbase + BN / 2 + g * 64 + h * 32, hi_u);
+          for (int sub = 0; sub < 2; ++sub) {
+            const int coff = g * 64 + hsel * 32 + sub * 16;
+            const int col0 = n0 + coff;
+            const int chunk0 = hsel * 4 + sub * 2;
+            uint32_t lo_u[16], hi_u[16];
+            tmem_ld16(tbase + coff, lo_u);
+            if (DUAL) tmem_ld16(tbase + BN / 2 + coff, hi_u);
             tmem_ld_wait();
             float* lo = reinterpret_cast<float*>(lo_u);
             float* hi = reinterpret_cast<float*>(hi_u);
-            float t3[32];
-            epilogue_math<EPI>(p, row, col0, lo, hi, t3);
+            float t3[16];
+            epilogue_math<EPI, 16>(p, row, col0, lo, hi, t3);
             if (DUAL) {
-              stage_bf16_half(buf0, rloc, h, t3);
-              stage_bf16_half(buf1, rloc, h, lo);
-              stage_bf16_half(buf2, rloc, h, hi);
+              stage_bf16_16(buf0, rloc, chunk0, t3);
+              stage_bf16_16(buf1, rloc, chunk0, lo);
+              stage_bf16_16(buf2, rloc, chunk0, hi);
             } else if (EPI == TASR_EPI_SILU) {
-              stage_bf16_half(buf0, rloc, h, t3);
-              stage_bf16_half(buf1, rloc, h, lo);
+              stage_bf16_16(buf0, rloc, chunk0, t3);
+              stage_bf16_16(buf1, rloc, chunk0, lo);
             } else if (EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) {
-              stage_bf16_half(buf0, rloc, h, lo);
-              stage_bf16_half(buf1, rloc, h, hi);
+              stage_bf16_16(buf0, rloc, chunk0, lo);
+              stage_bf16_16(buf1, rloc, chunk0, hi);
             } else {
-              stage_bf16_half(buf0, rloc, h, lo);
+              stage_bf16_16(buf0, rloc, chunk0, lo);
             }
           }
           fence_proxy_async_smem();
-          named_bar_sync(bar_id, EPI_GROUP_THREADS);
+          named_bar_sync(bar_id, G_SG_THREADS);
           if (leader) {
             const int c = n0 + g * 64;
             if (DUAL) {
@@ -260,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);  // all 256 epilogue threads: this accumulator may be overwritten
+      mbar_arrive(&tempty_bar[acc]);  // all 512 epilogue threads: this accumulator may be overwritten
     }
     if (leader) bulk_wait_all();
   }
@@ -278,13 +284,13 @@ __device__ __forceinline__ void dbg_store(void* base, long long ld, int is_f32, 
 }
 __global__ void gemm_debug_kernel(const bf16* A, long long lda, int a_mn, const bf16* B, long long ldb, int b_mn,
                                   GemmDev p, int dual) {
-  const int chunks = (p.N + 31) / 32;
+  const int chunks = (p.N + 15) / 16;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)p.M * chunks) return;
   const int row = (int)(gid / chunks);
-  const int col0 = (int)(gid % chunks) * 32;
-  float lo[32], hi[32], t3[32];
-  for (int i = 0; i < 32; ++i) {
+  const int col0 = (int)(gid % chunks) * 16;
+  float lo[16], hi[16], t3[16];
+  for (int i = 0; i < 16; ++i) {
     float s0 = 0.f, s1 = 0.f;
     const int n = col0 + i;
     if (n < p.N) {
@@ -302,18 +308,18 @@ __global__ void gemm_debug_kernel(const bf16* A, long long lda, int a_mn, const 
     hi[i] = s1;
   }
   switch (p.epi) {
-    case TASR_EPI_STORE: epilogue_math<TASR_EPI_STORE>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_RESID: epilogue_math<TASR_EPI_RESID>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_SWIGLU: epilogue_math<TASR_EPI_SWIGLU>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_GLU: epilogue_math<TASR_EPI_GLU>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_SILU: epilogue_math<TASR_EPI_SILU>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_SWIGLU_BWD: epilogue_math<TASR_EPI_SWIGLU_BWD>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_GLU_BWD: epilogue_math<TASR_EPI_GLU_BWD>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_SILU_BWD: epilogue_math<TASR_EPI_SILU_BWD>(p, row, col0, lo, hi, t3); break;
-    default: epilogue_math<TASR_EPI_ATOMIC>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_STORE: epilogue_math<TASR_EPI_STORE, 16>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_RESID: epilogue_math<TASR_EPI_RESID, 16>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_SWIGLU: epilogue_math<TASR_EPI_SWIGLU, 16>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_GLU: epilogue_math<TASR_EPI_GLU, 16>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_SILU: epilogue_math<TASR_EPI_SILU, 16>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_SWIGLU_BWD: epilogue_math<TASR_EPI_SWIGLU_BWD, 16>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_GLU_BWD: epilogue_math<TASR_EPI_GLU_BWD, 16>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_SILU_BWD: epilogue_math<TASR_EPI_SILU_BWD, 16>(p, row, col0, lo, hi, t3); break;
+    default: epilogue_math<TASR_EPI_ATOMIC, 16>(p, row, col0, lo, hi, t3); break;
   }
   const bool f32_out = (p.epi == TASR_EPI_RESID) || (p.epi == TASR_EPI_ATOMIC) || (p.epi == TASR_EPI_STORE && p.out_f32);
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < 16; ++i) {
     const int c = col0 + i;
     if (c >= p.N) break;
     switch (p.epi) {
@@ -468,7 +474,7 @@ int launch_tc(const tasr_gemm_args* a, GemmDev& p, cudaStream_t st) {
   p.tiles_n = cdiv(a->N, TILE_N);
   const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, tmO, tmO2, p);
+  kern<<<grid, G_THREADS, SMEM, st>>>(tmA, tmB, tmO, tmO2, p);
   TASR_CHECK_LAUNCH();
   return TASR_OK;
 }
@@ -547,7 +553,7 @@ extern "C" int tasr_gemm_bf16_debug(const tasr_gemm_args* a, tasr_stream_t strea
   p.kb_per_split = (a->K + BK - 1) / BK;
   p.splits = 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long total = (long long)a->M * ((a->N + 31) / 32);
+  const long long total = (long long)a->M * ((a->N + 15) / 16);
   gemm_debug_kernel<<<cdiv(total, 128), 128, 0, st>>>(reinterpret_cast<const bf16*>(a->A), a->lda, a->a_mn_major,
                                                       reinterpret_cast<const bf16*>(a->B), a->ldb, a->b_mn_major, p,
                                                       dual ? 1 : 0);

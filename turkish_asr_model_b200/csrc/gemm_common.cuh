@@ -10,6 +10,10 @@ constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 320;       // producer warp + MMA warp + 8 epilogue warps
 constexpr int EPI_THREADS = 256;
 constexpr int EPI_GROUP_THREADS = 128;  // one epilogue group = 4 warps = the 4 TMEM lane quarters
+// gemm.cu: 16 epilogue warps = 2 super-groups of 8 warps (each TMEM lane quarter twice: one warp per 32-column half)
+constexpr int G_THREADS = 576;
+constexpr int G_EPI_THREADS = 512;
+constexpr int G_SG_THREADS = 256;
 constexpr int STAGE_BYTES = 16384;  // 128 rows x 128 B
 
 struct GemmDev {
@@ -35,11 +39,13 @@ struct GemmDev {
   int tiles_m, tiles_n;
 };
 
-__device__ __forceinline__ void load_bf16_chunk(const bf16* src, float* v, int nvalid) {
-  if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+// W consecutive columns of one row (W = 16 or 32), vectorised when the chunk is full and 16-byte aligned
+template <int W>
+__device__ __forceinline__ void load_bf16_w(const bf16* src, float* v, int nvalid) {
+  if (nvalid == W && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < W / 8; ++i) {
       uint4 u = s4[i];
       float2 f;
       f = unpack_bf16x2(u.x); v[8 * i + 0] = f.x; v[8 * i + 1] = f.y;
@@ -49,26 +55,44 @@ __device__ __forceinline__ void load_bf16_chunk(const bf16* src, float* v, int n
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? __bfloat162float(src[i]) : 0.f;
+    for (int i = 0; i < W; ++i) v[i] = (i < nvalid) ? __bfloat162float(src[i]) : 0.f;
   }
 }
-__device__ __forceinline__ void load_f32_chunk(const float* src, float* v, int nvalid) {
-  if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+template <int W>
+__device__ __forceinline__ void load_f32_w(const float* src, float* v, int nvalid) {
+  if (nvalid == W && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < W / 4; ++i) {
       float4 f = s4[i];
       v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? src[i] : 0.f;
+    for (int i = 0; i < W; ++i) v[i] = (i < nvalid) ? src[i] : 0.f;
+  }
+}
+template <int W>
+__device__ __forceinline__ void load_bias_w(const float* __restrict__ bias, int col0, int nvalid, float* b) {
+  if (bias == nullptr) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) b[i] = 0.f;
+  } else if (nvalid == W && ((reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
+    const float4* s4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i) {
+      const float4 f = __ldg(s4 + i);
+      b[4 * i] = f.x; b[4 * i + 1] = f.y; b[4 * i + 2] = f.z; b[4 * i + 3] = f.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < W; ++i) b[i] = (i < nvalid) ? bias[col0 + i] : 0.f;
   }
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 // ------------------------------------------------------------------------------------------------
-// Fused epilogue math on one row chunk of 32 columns [col0, col0+32) of output row `row`.
+// Fused epilogue math on one row chunk of W columns [col0, col0+W) of output row `row`.
 //   in : lo = accumulator;  hi = paired accumulator (dual-B modes)
 //   out: lo = primary output, hi = second output, t3 = third output (see table below)
 //     STORE / RESID / SILU_BWD / ATOMIC : lo -> out
@@ -76,33 +100,15 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 //     SILU                              : t3 -> out (silu(z)), lo -> out2 (z)
 //     SWIGLU_BWD / GLU_BWD              : lo -> out[:, col], hi -> out[:, n_half+col]
 // Rows >= M or columns >= N produce don't-care values (clipped by the TMA store / masked by the caller).
-// The mode is a template parameter: only that mode's code is generated (the step is epilogue-bound for
-// the K = 256 GEMMs, and one 32-column chunk of a generic switch was ~15k SASS instructions).
+// The mode is a template parameter: only that mode's code is generated (the step is epilogue-bound for the
+// K = 256 GEMMs); W = 16 keeps the register footprint small enough for 16 epilogue warps per CTA.
 // ------------------------------------------------------------------------------------------------
-// bias for 32 consecutive columns (vectorised when the chunk is full and aligned)
-__device__ __forceinline__ void load_bias32(const float* __restrict__ bias, int col0, int nvalid, float* b) {
-  if (bias == nullptr) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) b[i] = 0.f;
-  } else if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
-    const float4* s4 = reinterpret_cast<const float4*>(bias + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 f = __ldg(s4 + i);
-      b[4 * i] = f.x; b[4 * i + 1] = f.y; b[4 * i + 2] = f.z; b[4 * i + 3] = f.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) b[i] = (i < nvalid) ? bias[col0 + i] : 0.f;
-  }
-}
-
-template <int EPI>
+template <int EPI, int W>
 __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col0, float* lo, float* hi, float* t3) {
-  const int nvalid = (row < p.M) ? max(0, min(32, p.N - col0)) : 0;
+  const int nvalid = (row < p.M) ? max(0, min(W, p.N - col0)) : 0;
   const long long r = row;
-  // dropout: pair-hash over the run of 16 pairs of this chunk (N % 32 == 0 is checked on the host, so the run
-  // starts at a multiple of 16 pairs and cannot cross a 2^32 boundary)
+  // dropout: pair-hash over the run of W/2 pairs of this chunk (N % 32 == 0 is checked on the host, so a run never
+  // crosses a 2^32 boundary of the pair index)
   uint32_t dbase = 0, dseed_hi = 0;
   if (p.drop_thresh) {
     const unsigned long long seed = p.seed_ptr ? p.seed + *p.seed_ptr : p.seed;
@@ -110,16 +116,17 @@ __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col
     dseed_hi = (uint32_t)(seed >> 32);
   }
   if (EPI == TASR_EPI_STORE) {
-    load_bias32(p.bias, col0, nvalid, t3);
+    load_bias_w<W>(p.bias, col0, nvalid, t3);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) lo[i] = p.alpha * (lo[i] + t3[i]);
+    for (int i = 0; i < W; ++i) lo[i] = p.alpha * (lo[i] + t3[i]);
   } else if (EPI == TASR_EPI_RESID) {
-    float bb[32];
-    load_bias32(p.bias, col0, nvalid, bb);
-    load_f32_chunk(reinterpret_cast<const float*>(p.aux) + r * p.ldaux + col0, t3, nvalid);
+    load_bias_w<W>(p.bias, col0, nvalid, t3);
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float v0 = lo[i] + bb[i], v1 = lo[i + 1] + bb[i + 1];
+    for (int i = 0; i < W; ++i) lo[i] += t3[i];
+    load_f32_w<W>(reinterpret_cast<const float*>(p.aux) + r * p.ldaux + col0, t3, nvalid);
+#pragma unroll
+    for (int i = 0; i < W; i += 2) {
+      float v0 = lo[i], v1 = lo[i + 1];
       if (p.drop_thresh) {
         float s0, s1;
         dropout_scale2_fast(dbase, dseed_hi, i >> 1, p.drop_thresh, p.drop_inv_keep, s0, s1);
@@ -129,14 +136,14 @@ __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col
       lo[i + 1] = t3[i + 1] + p.alpha * v1;
     }
   } else if (EPI == TASR_EPI_SWIGLU || EPI == TASR_EPI_GLU) {
-    load_bias32(p.bias, col0, nvalid, t3);
+    load_bias_w<W>(p.bias, col0, nvalid, t3);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) lo[i] = bf16_round(lo[i] + t3[i]);
-    load_bias32(p.bias ? p.bias + p.n_half : nullptr, col0, nvalid, t3);
+    for (int i = 0; i < W; ++i) lo[i] = bf16_round(lo[i] + t3[i]);
+    load_bias_w<W>(p.bias ? p.bias + p.n_half : nullptr, col0, nvalid, t3);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) hi[i] = bf16_round(hi[i] + t3[i]);
+    for (int i = 0; i < W; ++i) hi[i] = bf16_round(hi[i] + t3[i]);
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
+    for (int i = 0; i < W; i += 2) {
       float s0 = 1.f, s1 = 1.f;
       if (p.drop_thresh) dropout_scale2_fast(dbase, dseed_hi, i >> 1, p.drop_thresh, p.drop_inv_keep, s0, s1);
       const float v0 = (EPI == TASR_EPI_SWIGLU) ? siluf_(lo[i]) * hi[i] : lo[i] * sigmoidf_(hi[i]);
@@ -145,18 +152,18 @@ __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col
       t3[i + 1] = v1 * s1;
     }
   } else if (EPI == TASR_EPI_SILU) {
-    load_bias32(p.bias, col0, nvalid, t3);
+    load_bias_w<W>(p.bias, col0, nvalid, t3);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < W; ++i) {
       lo[i] = bf16_round(lo[i] + t3[i]);
       t3[i] = siluf_(lo[i]);
     }
   } else if (EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) {
     const bf16* ax = reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux;
-    load_bf16_chunk(ax + col0, hi, nvalid);             // g | a
-    load_bf16_chunk(ax + p.n_half + col0, t3, nvalid);  // v | b
+    load_bf16_w<W>(ax + col0, hi, nvalid);             // g | a
+    load_bf16_w<W>(ax + p.n_half + col0, t3, nvalid);  // v | b
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
+    for (int i = 0; i < W; i += 2) {
       float s0 = 1.f, s1 = 1.f;
       if (p.drop_thresh) dropout_scale2_fast(dbase, dseed_hi, i >> 1, p.drop_thresh, p.drop_inv_keep, s0, s1);
 #pragma unroll
@@ -176,13 +183,33 @@ __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col
       }
     }
   } else if (EPI == TASR_EPI_SILU_BWD) {
-    load_bf16_chunk(reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux + col0, t3, nvalid);
+    load_bf16_w<W>(reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux + col0, t3, nvalid);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) lo[i] = lo[i] * silu_gradf_(t3[i]);
+    for (int i = 0; i < W; ++i) lo[i] = lo[i] * silu_gradf_(t3[i]);
   } else if (EPI == TASR_EPI_ATOMIC) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) lo[i] *= p.alpha;
+    for (int i = 0; i < W; ++i) lo[i] *= p.alpha;
   }
+}
+
+// 16 columns of row r into a [128 rows x 128 B] swizzled staging buffer, starting at 16-byte chunk `chunk0`
+__device__ __forceinline__ void stage_bf16_16(uint8_t* buf, int r, int chunk0, const float* v) {
+  uint8_t* base = buf + r * 128;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(base + (((chunk0 + i) ^ (r & 7)) << 4)) = u;
+  }
+}
+__device__ __forceinline__ void stage_f32_16(uint8_t* buf, int r, int chunk0, const float* v) {
+  uint8_t* base = buf + r * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(base + (((chunk0 + i) ^ (r & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
 // staging writes: row r of a [128 rows x 128 B] buffer in the TMA 128-byte swizzle
