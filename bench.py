@@ -152,7 +152,7 @@ def cpu_reference_step_fn(threads):
         loss.backward()
         torch.nn.utils.clip_grad_norm_([p for p in params.values() if p.grad is not None], 1.0)
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     return step
 
@@ -269,20 +269,29 @@ def run_gpu(args):
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = L.lib().tasr_launch_count() + trainer.graph_kernel_launches - launches0
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
 
     # ---- end-to-end: pinned host buffers -> H2D -> step -> D2H of the loss, every step
     host_batches = []
     for b, db in zip(batches, dev_batches):
         host_batches.append({"waves": db["waves"].cpu().pin_memory(), "n_samples": b["n_samples"].pin_memory(),
                              "targets": b["targets"].pin_memory(), "target_lengths": b["target_lengths"].pin_memory()})
-    loss_host = torch.zeros(1).pin_memory()
+    # The loss of every step is copied to pinned host memory; the host reads it one step late (it waits for step
+    # i-1 while step i runs), so logging never drains the GPU.  Every step's H2D and D2H is inside the timed region.
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+    seen = {"n": 0, "last": 0.0}
 
     def e2e_step(i):
         hb = host_batches[i % n_distinct]
         l = trainer.train_step_waveforms(hb["waves"], hb["n_samples"], hb["targets"], hb["target_lengths"])
-        loss_host.copy_(l.reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the user reads the loss
+        k = seen["n"] & 1
+        loss_host[k].copy_(l.detach().reshape(1), non_blocking=True)
+        loss_evt[k].record()
+        if seen["n"] > 0:
+            loss_evt[k ^ 1].synchronize()  # the user reads the previous step's loss
+            seen["last"] = float(loss_host[k ^ 1])
+        seen["n"] += 1
         return hb
 
     for i in range(min(W, 3)):

@@ -183,7 +183,31 @@ class Trainer:
         st = self._static
         s_w = st["waves"][: B * nmax].view(B, nmax)
         s_t = st["targets"][: B * smax].view(B, smax)
-        s_w.copy_(waves, non_blocking=True)
+        if not waves.is_cuda:
+            # Host inputs: the (large) waveform H2D runs on a copy stream into one of two device staging buffers, so it
+            # overlaps with the previous step's graph still executing; the main stream then only does a D2D copy.
+            if "stage" not in st:
+                cap = self.max_graph_samples
+                st["stage"] = [torch.empty(B * cap, dtype=torch.float32, device=dev) for _ in range(2)]
+                st["stage_free"] = [torch.cuda.Event(), torch.cuda.Event()]
+                st["copy_stream"] = torch.cuda.Stream(device=dev)
+                st["step"] = 0
+                for e in st["stage_free"]:
+                    e.record()
+            k = st["step"] & 1
+            st["step"] += 1
+            stage = st["stage"][k][: B * nmax].view(B, nmax)
+            cs = st["copy_stream"]
+            cs.wait_event(st["stage_free"][k])  # the D2D that last read this staging buffer has run
+            with torch.cuda.stream(cs):
+                stage.copy_(waves, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(cs)
+            torch.cuda.current_stream().wait_event(done)
+            s_w.copy_(stage, non_blocking=True)
+            st["stage_free"][k].record()
+        else:
+            s_w.copy_(waves, non_blocking=True)
         st["n"].copy_(n_samples, non_blocking=True)
         s_t.copy_(targets, non_blocking=True)
         st["tl"].copy_(target_lengths, non_blocking=True)
