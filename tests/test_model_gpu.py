@@ -197,3 +197,25 @@ def test_standalone_submodules_match_oracle(cuda):
     assert w is None and _rel(a, oc.mqa_attention(x, sd, "b.attn.", 4, lens)) < 2e-2
     n = blk.norm_ff1(xd.detach())
     assert _rel(n, oc.group_norm_tokens(x, sd["b.norm_ff1.norm.weight"], sd["b.norm_ff1.norm.bias"])) < 1e-4
+
+
+def test_edge_cases_short_and_fully_masked(cuda):
+    """Ragged / degenerate inputs: B = 1, T' = 3, one utterance with L' = T // 4 = 0 (every key masked -> the
+    attention contributes 0 for that utterance by definition) and an infeasible CTC sample."""
+    torch.manual_seed(8)
+    model = TurkishASRModel(80, 128, 2, 1, 20, dropout=0.0).to(cuda).train()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 9, 80, generator=g)
+    out = model(x.to(cuda), torch.tensor([9]))
+    assert out.shape == (1, oc.encoder_frames(9), 20) and torch.isfinite(out.float()).all()
+    x2 = torch.randn(2, 40, 80, generator=g)
+    il = torch.tensor([40, 3])  # second utterance: L' = 0
+    out2 = model(x2.to(cuda), il)
+    assert torch.isfinite(out2.float()).all()
+    targets = torch.randint(1, 20, (2, 4), generator=g)
+    tl = torch.tensor([4, 4])  # sample 1 is infeasible (4 labels, 0 frames): zero loss and gradient (zero_infinity)
+    loss, nll, dl = L.ctc_loss_fwd_bwd(out2.detach(), targets.to(cuda), (il // 4).to(cuda), tl.to(cuda))
+    assert torch.isfinite(loss).all() and torch.isinf(nll[1]) and float(dl[1].float().abs().max()) == 0.0
+    out2.backward(dl)
+    for n, p in model.named_parameters():
+        assert p.grad is None or torch.isfinite(p.grad).all(), n
