@@ -36,30 +36,56 @@ __global__ void __launch_bounds__(NT) cast_f32_bf16_kernel(const float* __restri
   }
 }
 
-// out[c] += sum_r in[r][c]   (in: (M, N) bf16, row pitch ld)
+// out[c] += sum_r in[r][c]   (in: (M, N) bf16, row pitch ld).  blockDim = (32, 8): a warp covers 256 columns
+// (16 B per lane), 8 row lanes, 4 independent rows in flight per thread.
 __global__ void __launch_bounds__(NT) colsum_bf16_kernel(const bf16* __restrict__ in, long long M, int N, long long ld,
                                                          int rows_per_cta, float* __restrict__ out) {
-  // blockDim = (32, 8): x -> column pair, y -> row lane
-  const int cp = blockIdx.x * 32 + threadIdx.x;  // column pair index
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;  // first of this thread's 8 columns
   const long long r0 = (long long)blockIdx.y * rows_per_cta, r1 = min(M, r0 + (long long)rows_per_cta);
-  float2 acc = make_float2(0.f, 0.f);
-  const int c = cp * 2;
-  if (c + 1 < N) {
-    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
-      float2 v = __bfloat1622float2(*reinterpret_cast<const bf162*>(in + r * ld + c));
-      acc.x += v.x; acc.y += v.y;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (c + 8 <= N && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    long long r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(in + (r + 8 * k) * ld + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 f;
+        f = unpack_bf16x2(u[k].x); acc[0] += f.x; acc[1] += f.y;
+        f = unpack_bf16x2(u[k].y); acc[2] += f.x; acc[3] += f.y;
+        f = unpack_bf16x2(u[k].z); acc[4] += f.x; acc[5] += f.y;
+        f = unpack_bf16x2(u[k].w); acc[6] += f.x; acc[7] += f.y;
+      }
     }
-  } else if (c < N) {
-    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc.x += __bfloat162float(in[r * ld + c]);
+    for (; r < r1; r += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(in + r * ld + c);
+      float2 f;
+      f = unpack_bf16x2(u.x); acc[0] += f.x; acc[1] += f.y;
+      f = unpack_bf16x2(u.y); acc[2] += f.x; acc[3] += f.y;
+      f = unpack_bf16x2(u.z); acc[4] += f.x; acc[5] += f.y;
+      f = unpack_bf16x2(u.w); acc[6] += f.x; acc[7] += f.y;
+    }
+  } else {
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (c + i < N) acc[i] += __bfloat162float(in[r * ld + c + i]);
   }
-  __shared__ float2 sh[8][32];
-  sh[threadIdx.y][threadIdx.x] = acc;
+  __shared__ float sh[8][32][9];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sh[threadIdx.y][threadIdx.x][i] = acc[i];
   __syncthreads();
-  if (threadIdx.y == 0) {
-    for (int y = 1; y < 8; ++y) { acc.x += sh[y][threadIdx.x].x; acc.y += sh[y][threadIdx.x].y; }
-    if (c < N) atomicAdd(out + c, acc.x);
-    if (c + 1 < N) atomicAdd(out + c + 1, acc.y);
-  }
+  // 256 threads: one column each
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  const int lane_x = t >> 3, i = t & 7;
+  float s = 0.f;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) s += sh[y][lane_x][i];
+  const int col = (blockIdx.x * 32 + lane_x) * 8 + i;
+  if (col < N) atomicAdd(out + col, s);
 }
 
 // In-place NeoX-style RoPE on the first `rot_cols` columns of each row (blocks of 64: H query heads and
@@ -99,9 +125,9 @@ extern "C" int tasr_cast_f32_bf16(const float* in, void* out, int64_t n, float a
 
 extern "C" int tasr_colsum_bf16(const void* in, int64_t M, int N, int64_t ld, float* out, tasr_stream_t stream) {
   if (M <= 0 || N <= 0 || (ld & 1)) return TASR_ERR_SHAPE;
-  const int col_blocks = cdiv(N, 64);
-  int row_blocks = (int)((M + 63) / 64);
-  if (row_blocks > 1184 / col_blocks) row_blocks = 1184 / col_blocks;
+  const int col_blocks = cdiv(N, 256);
+  int row_blocks = (int)((M + 127) / 128);
+  if (row_blocks > 888 / col_blocks) row_blocks = 888 / col_blocks;
   if (row_blocks < 1) row_blocks = 1;
   const int rows_per_cta = (int)((M + row_blocks - 1) / row_blocks);
   row_blocks = (int)((M + rows_per_cta - 1) / rows_per_cta);
