@@ -1,8 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 1200 python -m pytest tests -q -m gpu --timeout 600 -x -k "colsum or model or golden" > gpurun_out/test.log 2>&1
+timeout -s KILL 1200 python -m pytest tests -q -m gpu --timeout 600 -x -k "gemm or model or golden" > gpurun_out/test.log 2>&1
 echo "exit $?" >> gpurun_out/test.log
 tail -5 gpurun_out/test.log
+python tools/prof_gemm.py all 0.1 2>&1 | tee gpurun_out/gemm_shapes.log
 timeout -s KILL 900 python bench.py --steps 24 --warmup 12 --no-cpu > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -1 gpurun_out/bench.log | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e'])"; tail -5 gpurun_out/bench.err
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e'], d['roofline']['frac'])"; tail -5 gpurun_out/bench.err

@@ -153,6 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int bar_id = 1 + sg;
     uint8_t* ring_base = sC + sg * RINGG * STAGE_BYTES;
     constexpr bool F32_MODE = (EPI == TASR_EPI_RESID || EPI == TASR_EPI_ATOMIC);
+    constexpr bool HAS_AUX_BF16 = (EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD || EPI == TASR_EPI_SILU_BWD);
     const bool f32_out = F32_MODE || (EPI == TASR_EPI_STORE && p.out_f32);
     const bool direct_atomic = (EPI == TASR_EPI_ATOMIC) && (p.remap_p0 > 0);
     uint32_t tcount = 0, ring = 0;
@@ -162,6 +163,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = m_tile * BM, n0 = n_tile * TILE_N;
       const int row = m0 + rloc;
       const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+      // saved-tensor operands of this thread's first column group: in flight while we wait for the accumulator
+      AuxBf16 ax_first[2];
+      AuxF32 res_first[2];
+      if (HAS_AUX_BF16) {
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) preload_aux_bf16<EPI>(p, row, n0 + sg * 64 + hsel * 32 + sub * 16, ax_first[sub]);
+      }
+      if (EPI == TASR_EPI_RESID) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) preload_aux_f32(p, row, n0 + sg * 64 + u * 32 + hsel * 16, res_first[u]);
+      }
       mbar_wait(&tfull_bar[acc], aph);
       __syncwarp();
       tc_fence_after();
@@ -171,15 +183,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (n0 + g * 64 >= p.N) break;              // fully out of range (uniform across the super-group)
         if (f32_out) {
           if (EPI == TASR_EPI_STORE || F32_MODE) {
-#pragma unroll 1
+            AuxF32 res[2];
+            if (EPI == TASR_EPI_RESID) {
+              if (g == sg) { res[0] = res_first[0]; res[1] = res_first[1]; }
+              else {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) preload_aux_f32(p, row, n0 + g * 64 + u * 32 + hsel * 16, res[u]);
+              }
+            }
+#pragma unroll
             for (int u = 0; u < 2; ++u) {  // two 32-column fp32 staging buffers per group; this warp set: 16 of the 32
               const int col0 = n0 + g * 64 + u * 32 + hsel * 16;
               uint32_t lo_u[16];
               tmem_ld16(tbase + g * 64 + u * 32 + hsel * 16, lo_u);
               tmem_ld_wait();
               float* lo = reinterpret_cast<float*>(lo_u);
-              float t3[16];
-              epilogue_math<EPI, 16>(p, row, col0, lo, lo, t3);
+              if (EPI == TASR_EPI_RESID) {
+                epilogue_resid16(p, row, col0, lo, res[u]);
+              } else {
+                float t3[16];
+                epilogue_math<EPI, 16>(p, row, col0, lo, lo, t3);
+              }
               if (direct_atomic) {
                 if (row < p.M) {
                   float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo;
@@ -211,12 +235,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else if (!F32_MODE) {
           // bf16 outputs: NBUF 64-column staging buffers per group
+          AuxBf16 ax[2];
+          if (HAS_AUX_BF16) {
+            if (g == sg) { ax[0] = ax_first[0]; ax[1] = ax_first[1]; }
+            else {
+#pragma unroll
+              for (int sub = 0; sub < 2; ++sub) preload_aux_bf16<EPI>(p, row, n0 + g * 64 + hsel * 32 + sub * 16, ax[sub]);
+            }
+          }
           if (leader) bulk_wait_read<RINGG - NBUF>();
           named_bar_sync(bar_id, G_SG_THREADS);
           uint8_t* buf0 = ring_base + (ring % RINGG) * STAGE_BYTES;
           uint8_t* buf1 = ring_base + ((ring + 1) % RINGG) * STAGE_BYTES;
           uint8_t* buf2 = ring_base + ((ring + 2) % RINGG) * STAGE_BYTES;
-#pragma unroll 1
+#pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             const int coff = g * 64 + hsel * 32 + sub * 16;
             const int col0 = n0 + coff;
@@ -228,7 +260,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* lo = reinterpret_cast<float*>(lo_u);
             float* hi = reinterpret_cast<float*>(hi_u);
             float t3[16];
-            epilogue_math<EPI, 16>(p, row, col0, lo, hi, t3);
+            if (HAS_AUX_BF16) epilogue_bwd16<EPI>(p, row, col0, lo, hi, ax[sub]);
+            else epilogue_math<EPI, 16>(p, row, col0, lo, hi, t3);
             if (DUAL) {
               stage_bf16_16(buf0, rloc, chunk0, t3);
               stage_bf16_16(buf1, rloc, chunk0, lo);
@@ -410,6 +443,11 @@ int fill_dev(const tasr_gemm_args* a, GemmDev* p, bool* dual) {
   p->alpha = a->alpha; p->n_half = a->n_half;
   p->drop_thresh = tasr_drop_thresh16(a->drop_p);
   p->drop_inv_keep = tasr_drop_inv_keep(p->drop_thresh);
+  if ((a->epilogue == TASR_EPI_SWIGLU_BWD || a->epilogue == TASR_EPI_GLU_BWD || a->epilogue == TASR_EPI_SILU_BWD) &&
+      ((a->N & 15) || (a->ldaux & 7) || (reinterpret_cast<uintptr_t>(a->aux) & 15) || (a->n_half & 7)))
+    return TASR_ERR_ALIGN;
+  if (a->epilogue == TASR_EPI_RESID && ((a->N & 15) || (a->ldaux & 3) || (reinterpret_cast<uintptr_t>(a->aux) & 15)))
+    return TASR_ERR_ALIGN;
   if (p->drop_thresh && (a->N & 31)) return TASR_ERR_SHAPE;  // the pair-hash dropout mask is generated in runs of 32 columns
   p->seed = a->seed;
   p->seed_ptr = g_tasr_seed_ptr;

@@ -92,6 +92,99 @@ __device__ __forceinline__ void load_bias_w(const float* __restrict__ bias, int 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 // ------------------------------------------------------------------------------------------------
+// Operand pre-loading for the epilogues that read a saved tensor (16-column pieces).  The loads are issued before
+// the thread waits for the accumulator / the staging barrier so that their (HBM) latency overlaps with those waits.
+// ------------------------------------------------------------------------------------------------
+struct AuxBf16 {  // 16 bf16 of the first half (g | a | z) and 16 of the second half (v | b)
+  uint4 a[2], b[2];
+};
+template <int EPI>
+__device__ __forceinline__ void preload_aux_bf16(const GemmDev& p, int row, int col0, AuxBf16& x) {
+  x.a[0] = x.a[1] = x.b[0] = x.b[1] = make_uint4(0, 0, 0, 0);
+  if (row < p.M && col0 + 16 <= p.N) {
+    const bf16* ax = reinterpret_cast<const bf16*>(p.aux) + (long long)row * p.ldaux + col0;
+    const uint4* s0 = reinterpret_cast<const uint4*>(ax);
+    x.a[0] = s0[0]; x.a[1] = s0[1];
+    if (EPI != TASR_EPI_SILU_BWD) {
+      const uint4* s1 = reinterpret_cast<const uint4*>(ax + p.n_half);
+      x.b[0] = s1[0]; x.b[1] = s1[1];
+    }
+  }
+}
+__device__ __forceinline__ float bf16_at(const uint4* q, int k) {  // element k (0..15) of 2 packed uint4
+  const uint32_t w = reinterpret_cast<const uint32_t*>(q)[k >> 1];
+  return __uint_as_float((k & 1) ? (w & 0xFFFF0000u) : (w << 16));
+}
+// math of the *_BWD epilogues on a pre-loaded piece: lo = accumulator in, lo/hi = outputs
+template <int EPI>
+__device__ __forceinline__ void epilogue_bwd16(const GemmDev& p, int row, int col0, float* lo, float* hi, const AuxBf16& x) {
+  uint32_t dbase = 0, dseed_hi = 0;
+  if (p.drop_thresh) {
+    const unsigned long long seed = p.seed_ptr ? p.seed + *p.seed_ptr : p.seed;
+    dbase = tasr_hash_pair_base(seed, (unsigned long long)((long long)row * p.N + col0) >> 1);
+    dseed_hi = (uint32_t)(seed >> 32);
+  }
+  if (EPI == TASR_EPI_SILU_BWD) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) lo[i] = lo[i] * silu_gradf_(bf16_at(x.a, i));
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    float s0 = 1.f, s1 = 1.f;
+    if (p.drop_thresh) dropout_scale2_fast(dbase, dseed_hi, i >> 1, p.drop_thresh, p.drop_inv_keep, s0, s1);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = i + j;
+      const float d = lo[k] * (j == 0 ? s0 : s1);
+      const float g = bf16_at(x.a, k), v = bf16_at(x.b, k);
+      if (EPI == TASR_EPI_SWIGLU_BWD) {
+        const float sg = sigmoidf_(g);
+        lo[k] = d * v * sg * (1.f + g * (1.f - sg));  // d/dg
+        hi[k] = d * g * sg;                            // d/dv
+      } else {
+        const float sv = sigmoidf_(v);
+        lo[k] = d * sv;                                // d/da
+        hi[k] = d * g * sv * (1.f - sv);               // d/db
+      }
+    }
+  }
+}
+struct AuxF32 {  // 16 fp32 residual values
+  float4 v[4];
+};
+__device__ __forceinline__ void preload_aux_f32(const GemmDev& p, int row, int col0, AuxF32& x) {
+  x.v[0] = x.v[1] = x.v[2] = x.v[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < p.M && col0 + 16 <= p.N) {
+    const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (long long)row * p.ldaux + col0);
+    x.v[0] = s[0]; x.v[1] = s[1]; x.v[2] = s[2]; x.v[3] = s[3];
+  }
+}
+__device__ __forceinline__ void epilogue_resid16(const GemmDev& p, int row, int col0, float* lo, const AuxF32& x) {
+  const int nvalid = (row < p.M) ? max(0, min(16, p.N - col0)) : 0;
+  float bb[16];
+  load_bias_w<16>(p.bias, col0, nvalid, bb);
+  uint32_t dbase = 0, dseed_hi = 0;
+  if (p.drop_thresh) {
+    const unsigned long long seed = p.seed_ptr ? p.seed + *p.seed_ptr : p.seed;
+    dbase = tasr_hash_pair_base(seed, (unsigned long long)((long long)row * p.N + col0) >> 1);
+    dseed_hi = (uint32_t)(seed >> 32);
+  }
+  const float* res = reinterpret_cast<const float*>(x.v);
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    float v0 = lo[i] + bb[i], v1 = lo[i + 1] + bb[i + 1];
+    if (p.drop_thresh) {
+      float s0, s1;
+      dropout_scale2_fast(dbase, dseed_hi, i >> 1, p.drop_thresh, p.drop_inv_keep, s0, s1);
+      v0 *= s0; v1 *= s1;
+    }
+    lo[i] = res[i] + p.alpha * v0;
+    lo[i + 1] = res[i + 1] + p.alpha * v1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused epilogue math on one row chunk of W columns [col0, col0+W) of output row `row`.
 //   in : lo = accumulator;  hi = paired accumulator (dual-B modes)
 //   out: lo = primary output, hi = second output, t3 = third output (see table below)
