@@ -18,10 +18,10 @@ batches = bench.make_batches(6, 0, 1)
 db = []
 for b in batches:
     db.append((bench.synth_waves(b, dev), b["n_samples"].to(dev), b["targets"].to(dev), b["target_lengths"].to(dev), 1 + int(b["n_samples"].max()) // 160))
-for i in range(3):
-    tr.train_step_waveforms(*db[i][:4], tmax=db[i][4])
+for i in range(12):
+    tr.train_step_waveforms(*db[i % 6][:4], tmax=db[i % 6][4])
 torch.cuda.synchronize()
-N = 12
+N = 24
 t0 = time.perf_counter()
 for i in range(N):
     b = db[i % 6]
@@ -30,19 +30,3 @@ t1 = time.perf_counter()
 torch.cuda.synchronize()
 t2 = time.perf_counter()
 print("host issue ms/step %.2f   total ms/step %.2f   tmax %s" % ((t1 - t0) / N * 1e3, (t2 - t0) / N * 1e3, [b[4] for b in db]))
-# per-GEMM device time with a sync before each launch (no launch gaps inside the event pair)
-L.GEMM_PROFILE = []
-b = db[0]
-orig = L.lib().tasr_gemm_bf16
-tr.train_step_waveforms(*b[:4], tmax=b[4])
-torch.cuda.synchronize()
-prof, L.GEMM_PROFILE = L.GEMM_PROFILE, None
-import collections
-agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
-for fl, e0, e1, key in prof:
-    ms = e0.elapsed_time(e1)
-    agg[key][0] += 1; agg[key][1] += ms; agg[key][2] += fl
-tot = sum(v[1] for v in agg.values())
-print("gemm total ms %.2f (event pairs, includes launch gaps if host-bound)" % tot)
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
-    print("M=%6d N=%5d K=%6d epi=%d amn=%d bmn=%d  n=%3d  %.3f ms  %.0f TFLOP/s" % (k + (v[0], v[1], v[2] / v[1] / 1e9)))

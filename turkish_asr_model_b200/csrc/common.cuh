@@ -25,6 +25,24 @@ int tasr_set_cuda_error(cudaError_t e);  // records the message, returns TASR_ER
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
 
+#ifdef __CUDACC__
+// launch with the programmatic-dependent-launch attribute (the kernel must call grid_dependency_wait())
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#endif
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline long long imin64(long long a, long long b) { return a < b ? a : b; }
 
@@ -277,6 +295,10 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor drains; everything before this wait (barrier init, TMEM allocation, descriptor prefetch)
+// overlaps with the predecessor's tail, everything after it sees the predecessor's memory.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -89,6 +89,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dependency_wait();  // prologue above overlaps the previous kernel's tail (PDL)
 
   auto class_map = [&](int idx) -> const CUtensorMap* {
     return idx == 0 ? &cm0 : (idx == 1 ? &cm1 : (idx == 2 ? &cm2 : &cm3));
@@ -551,7 +552,8 @@ int launch_conv(const CUtensorMap* cm, const CUtensorMap& tmW, const CUtensorMap
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
   const int grid = (int)(total < g_sms ? total : g_sms);
-  kern<<<grid, GEMM_THREADS, SMEM, st>>>(cm[0], cm[1], cm[2], cm[3], tmW, tmZ, tmY, p);
+  cudaError_t lerr = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)SMEM, st, cm[0], cm[1], cm[2], cm[3], tmW, tmZ, tmY, p);
+  if (lerr != cudaSuccess) return tasr_set_cuda_error(lerr);
   TASR_CHECK_LAUNCH();
   return TASR_OK;
 }

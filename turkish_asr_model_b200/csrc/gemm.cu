@@ -71,6 +71,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dependency_wait();  // prologue above overlaps the previous kernel's tail (PDL)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -512,7 +513,8 @@ int launch_tc(const tasr_gemm_args* a, GemmDev& p, cudaStream_t st) {
   p.tiles_n = cdiv(a->N, TILE_N);
   const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  kern<<<grid, G_THREADS, SMEM, st>>>(tmA, tmB, tmO, tmO2, p);
+  cudaError_t lerr = launch_pdl(kern, dim3(grid), dim3(G_THREADS), (size_t)SMEM, st, tmA, tmB, tmO, tmO2, p);
+  if (lerr != cudaSuccess) return tasr_set_cuda_error(lerr);
   TASR_CHECK_LAUNCH();
   return TASR_OK;
 }
