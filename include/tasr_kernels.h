@@ -131,7 +131,9 @@ int tasr_mel_forward(const float* wave, int64_t wave_ld, const int32_t* n_sample
  * Replaces: model/conformer.py:45-49 TransposeGroupNorm.forward (transpose + native_group_norm +
  *   transpose), 5 uses per block (:121,124,78,133,135), and its backward.
  *   stats (B, G, 2) fp32 = (mean, rstd) saved for backward.  out is bf16 (GEMM operand) or fp32.
- *   bwd: dres (B,T,d) fp32 = (accumulate ? dres : 0) + dx;  dgamma/dbeta (d) are accumulated (+=).
+ *   bwd: dres (B,T,d) fp32 = (accumulate ? dres : 0) + dx;  dgamma/dbeta (d) are accumulated (+=);
+ *        cast_out (bf16, may be NULL) = bf16(cast_alpha * dropout_mask(cast_seed) * dres): the operand of the
+ *        next backward GEMMs, written in the same pass (same mask function as tasr_cast_f32_bf16).
  * Requires d/G % 4 == 0 and d/4 a divisor of 256.
  * ---------------------------------------------------------------------------------------------- */
 size_t tasr_groupnorm_workspace_bytes(int B, int T, int d);
@@ -139,7 +141,8 @@ int tasr_groupnorm_fwd(const float* x, int B, int T, int d, int G, float eps, co
                        void* out, int out_bf16, float* stats, void* workspace, size_t workspace_bytes,
                        tasr_stream_t stream);
 int tasr_groupnorm_bwd(const void* dy, int dy_bf16, const float* x, int B, int T, int d, int G, const float* stats,
-                       const float* gamma, float* dres, int accumulate, float* dgamma, float* dbeta, void* workspace,
+                       const float* gamma, float* dres, int accumulate, float* dgamma, float* dbeta, void* cast_out,
+                       float cast_alpha, float cast_drop_p, uint64_t cast_seed, void* workspace,
                        size_t workspace_bytes, tasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

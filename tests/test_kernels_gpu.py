@@ -57,6 +57,12 @@ def test_groupnorm_fwd_bwd(cuda, B, T, d, out_bf16):
     L.groupnorm_bwd(dy_dev, x.to(cuda), 32, stats, gamma.to(cuda), dres2, False, None, None)
     torch.cuda.synchronize()
     assert rel_err(dres2, xd.grad) < 2e-5
+    # fused cast: same bits as the stand-alone cast kernel (scale + counter-based dropout mask) on the new dres
+    dres3 = torch.empty(B, T, d, device=cuda)
+    fused = L.groupnorm_bwd(dy_dev, x.to(cuda), 32, stats, gamma.to(cuda), dres3, False, None, None, cast=(0.5, 0.1, 1234))
+    sep = L.cast_bf16(dres3, alpha=0.5, drop_p=0.1, seed=1234)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, sep) and torch.equal(dres3, dres2)
 
 
 # ------------------------------------------------------------------ depthwise conv + BatchNorm + SiLU

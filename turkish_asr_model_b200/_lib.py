@@ -29,7 +29,7 @@ _SIGNATURES = {
     "tasr_mel_forward": (I, [P, L, P, I, I, P, P, P, I, I, I, I, P, P, Z, P]),
     "tasr_groupnorm_workspace_bytes": (Z, [I, I, I]),
     "tasr_groupnorm_fwd": (I, [P, I, I, I, I, F, P, P, P, I, P, P, Z, P]),
-    "tasr_groupnorm_bwd": (I, [P, I, P, I, I, I, I, P, P, P, I, P, P, P, Z, P]),
+    "tasr_groupnorm_bwd": (I, [P, I, P, I, I, I, I, P, P, P, I, P, P, P, F, F, U64, P, Z, P]),
     "tasr_dwconv_bn_parts": (I, [I, I]),
     "tasr_dwconv31_fwd": (I, [P, I, I, I, P, P, P, P, P]),
     "tasr_dwconv31_bwd": (I, [P, P, P, I, I, I, P, P, P, P, P, P]),
@@ -212,14 +212,22 @@ def groupnorm_fwd(x, G, gamma, beta, eps=1e-5, out_bf16=True):
     return y, stats
 
 
-def groupnorm_bwd(dy, x, G, stats, gamma, dres, accumulate, dgamma, dbeta):
-    """dres (B,T,d) fp32 (+)= dx; dgamma/dbeta += ."""
+def groupnorm_bwd(dy, x, G, stats, gamma, dres, accumulate, dgamma, dbeta, cast=None):
+    """dres (B,T,d) fp32 (+)= dx; dgamma/dbeta += .  cast = (alpha, drop_p, seed) additionally returns
+    bf16(alpha * dropout_mask * dres) written in the same pass."""
     require_cuda(dy, x, dres)
     B, T, d = x.shape
     wsb = lib().tasr_groupnorm_workspace_bytes(B, T, d)
     ws = workspace(wsb, x.device)
+    cast_out = None
+    alpha, drop_p, seed = 1.0, 0.0, 0
+    if cast is not None:
+        alpha, drop_p, seed = cast
+        cast_out = torch.empty(B, T, d, dtype=torch.bfloat16, device=x.device)
     check(lib().tasr_groupnorm_bwd(ptr(dy), int(dy.dtype == torch.bfloat16), ptr(x), B, T, d, G, ptr(stats), ptr(gamma),
-                                   ptr(dres), int(accumulate), ptr(dgamma), ptr(dbeta), ptr(ws), wsb, stream_ptr()))
+                                   ptr(dres), int(accumulate), ptr(dgamma), ptr(dbeta), ptr(cast_out), alpha, drop_p, seed,
+                                   ptr(ws), wsb, stream_ptr()))
+    return cast_out
 
 
 # ---------------------------------------------------------------------------------------------

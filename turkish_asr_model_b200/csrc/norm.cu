@@ -148,8 +148,12 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const void* __restrict
                                                           const float* __restrict__ partial, int nchunk_stats,
                                                           const float* __restrict__ gamma, float* __restrict__ dres,
                                                           int accumulate, float* __restrict__ dgamma,
-                                                          float* __restrict__ dbeta) {
+                                                          float* __restrict__ dbeta, bf16* __restrict__ cast_out,
+                                                          float cast_alpha, uint32_t cast_thresh, float cast_inv_keep,
+                                                          unsigned long long cast_seed,
+                                                          const unsigned long long* __restrict__ seed_ptr) {
   const int b = blockIdx.y;
+  if (cast_thresh && seed_ptr) cast_seed += *seed_ptr;
   extern __shared__ float sh_dyn[];  // d floats: a_c ; d floats: c_c ; G: S1 ; G: S2
   float* sh_a = sh_dyn;
   float* sh_c = sh_dyn + d;
@@ -205,6 +209,16 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const void* __restrict
       r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
     }
     *reinterpret_cast<float4*>(dres + off) = r;
+    if (cast_out != nullptr) {  // fused "dy = bf16(alpha * dropout_mask * dres)" for the next backward GEMMs
+      float4 c4 = make_float4(r.x * cast_alpha, r.y * cast_alpha, r.z * cast_alpha, r.w * cast_alpha);
+      if (cast_thresh) {
+        float s0, s1, s2, s3;
+        dropout_scale2(cast_seed, (unsigned long long)off, cast_thresh, cast_inv_keep, s0, s1);
+        dropout_scale2(cast_seed, (unsigned long long)off + 2, cast_thresh, cast_inv_keep, s2, s3);
+        c4.x *= s0; c4.y *= s1; c4.z *= s2; c4.w *= s3;
+      }
+      st4_bf16(cast_out + off, c4);
+    }
   }
 }
 
@@ -386,7 +400,11 @@ extern "C" int tasr_groupnorm_fwd(const float* x, int B, int T, int d, int G, fl
 
 extern "C" int tasr_groupnorm_bwd(const void* dy, int dy_bf16, const float* x, int B, int T, int d, int G,
                                   const float* stats, const float* gamma, float* dres, int accumulate, float* dgamma,
-                                  float* dbeta, void* workspace, size_t workspace_bytes, tasr_stream_t stream) {
+                                  float* dbeta, void* cast_out, float cast_alpha, float cast_drop_p, uint64_t cast_seed,
+                                  void* workspace, size_t workspace_bytes, tasr_stream_t stream) {
+  const uint32_t cthresh = tasr_drop_thresh16(cast_drop_p);
+  const float cinv = tasr_drop_inv_keep(cthresh);
+  bf16* cout_ = reinterpret_cast<bf16*>(cast_out);
   if (!gn_shape_ok(d, G) || B <= 0 || T <= 0) return TASR_ERR_SHAPE;
   if (workspace_bytes < tasr_groupnorm_workspace_bytes(B, T, d)) return TASR_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -398,12 +416,12 @@ extern "C" int tasr_groupnorm_bwd(const void* dy, int dy_bf16, const float* x, i
     gn_bwd_stats_kernel<true><<<grid, NT, 0, st>>>(dy, x, T, d, G, rows, stats, partial);
     TASR_CHECK_LAUNCH();
     gn_bwd_apply_kernel<true><<<grid, NT, sm, st>>>(dy, x, T, d, G, rows, stats, partial, nchunk, gamma, dres, accumulate,
-                                                    dgamma, dbeta);
+                                                    dgamma, dbeta, cout_, cast_alpha, cthresh, cinv, cast_seed, g_tasr_seed_ptr);
   } else {
     gn_bwd_stats_kernel<false><<<grid, NT, 0, st>>>(dy, x, T, d, G, rows, stats, partial);
     TASR_CHECK_LAUNCH();
     gn_bwd_apply_kernel<false><<<grid, NT, sm, st>>>(dy, x, T, d, G, rows, stats, partial, nchunk, gamma, dres, accumulate,
-                                                     dgamma, dbeta);
+                                                     dgamma, dbeta, cout_, cast_alpha, cthresh, cinv, cast_seed, g_tasr_seed_ptr);
   }
   TASR_CHECK_LAUNCH();
   return TASR_OK;

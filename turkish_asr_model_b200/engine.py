@@ -312,20 +312,20 @@ class ConformerEngine:
         L.gemm(out_f, in_f, tokens, dy, dy.stride(0), x, x.stride(0), L.EPI_ATOMIC, gw, in_f, a_mn=1, b_mn=1,
                split_k=_split_k(out_f, in_f, tokens), remap_p0=p0, remap_p1=p1)
 
-    def _ff_backward(self, pre, dres, saved, xn, M, drop, seed):
-        """Backward of x + 0.5*dropout(linear2(dropout(swiglu(linear1(xn))))); returns d xn (bf16)."""
+    def _ff_backward(self, pre, dy, saved, xn, M, drop, seed):
+        """Backward of x + 0.5*dropout(linear2(dropout(swiglu(linear1(xn))))); dy = bf16(0.5 * mask * dres);
+        returns d xn (bf16)."""
         d, dff = self.d, self.dff
         S, Gv = self.S, self.Gv
         gv, h = saved
-        dy = L.cast_bf16(dres, alpha=0.5, drop_p=drop, seed=seed + 1)
         self._wgrad(dy, h, d, dff, M, Gv(pre + "linear2.weight"))
         L.colsum_add(dy, Gv(pre + "linear2.bias"))
-        dgv = torch.empty(M, 2 * dff, dtype=torch.bfloat16, device=dres.device)
+        dgv = torch.empty(M, 2 * dff, dtype=torch.bfloat16, device=dy.device)
         L.gemm(M, dff, d, dy, d, S(pre + "linear2.weight"), dff, L.EPI_SWIGLU_BWD, dgv, 2 * dff, b_mn=1, aux=gv,
                ldaux=2 * dff, n_half=dff, drop_p=drop, seed=seed)
         self._wgrad(dgv, xn, 2 * dff, d, M, Gv(pre + "linear1.weight"))
         L.colsum_add(dgv, Gv(pre + "linear1.bias"))
-        dxn = torch.empty(M, d, dtype=torch.bfloat16, device=dres.device)
+        dxn = torch.empty(M, d, dtype=torch.bfloat16, device=dy.device)
         L.gemm(M, d, 2 * dff, dgv, 2 * dff, S(pre + "linear1.weight"), d, L.EPI_STORE, dxn, d, b_mn=1)
         return dxn
 
@@ -338,17 +338,18 @@ class ConformerEngine:
         seed = sv["seed"]
         d3 = dres.view(B, T, d)
 
-        def gn_bwd(dy, xin, st, name, accumulate):
-            L.groupnorm_bwd(dy.view(B, T, d), xin.view(B, T, d), G, st, P(pre + name + ".weight"), d3, accumulate,
-                            Gv(pre + name + ".weight"), Gv(pre + name + ".bias"))
+        def gn_bwd(dy, xin, st, name, accumulate, cast=None):
+            out = L.groupnorm_bwd(dy.view(B, T, d), xin.view(B, T, d), G, st, P(pre + name + ".weight"), d3, accumulate,
+                                  Gv(pre + name + ".weight"), Gv(pre + name + ".bias"), cast=cast)
+            return None if out is None else out.view(M, d)
 
+        # Every GroupNorm backward also emits the bf16 operand ("dy") of the backward GEMMs that follow it.
         # 5. final_norm (in place: dres <- d x4)
-        gn_bwd(dres, sv["x4"], sv["st5"], "final_norm.norm", False)
+        dy = gn_bwd(dres, sv["x4"], sv["st5"], "final_norm.norm", False, cast=(0.5, drop, seed + 4 + 1))
         # 4. ff2
-        dxn = self._ff_backward(pre + "ff2.", dres, sv["ff2"], sv["xn4"].view(M, d), M, drop, seed + 4)
-        gn_bwd(dxn, sv["x3"], sv["st4"], "norm_ff2.norm", True)
+        dxn = self._ff_backward(pre + "ff2.", dy, sv["ff2"], sv["xn4"].view(M, d), M, drop, seed + 4)
+        dy = gn_bwd(dxn, sv["x3"], sv["st4"], "norm_ff2.norm", True, cast=(1.0, 0.0, 0))
         # 3. conv module
-        dy = L.cast_bf16(dres)
         self._wgrad(dy, sv["s"].view(M, d), d, d, M, Gv(pre + "conv.pointwise_conv2.weight", (d, d)))
         L.colsum_add(dy, Gv(pre + "conv.pointwise_conv2.bias"))
         ds = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
@@ -362,9 +363,8 @@ class ConformerEngine:
         L.colsum_add(dab, Gv(pre + "conv.pointwise_conv1.bias"))
         dxn = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
         L.gemm(M, d, 2 * d, dab, 2 * d, S(pre + "conv.pointwise_conv1.weight", (2 * d, d)), d, L.EPI_STORE, dxn, d, b_mn=1)
-        gn_bwd(dxn, sv["x2"], sv["st3"], "conv.norm.norm", True)
+        dy = gn_bwd(dxn, sv["x2"], sv["st3"], "conv.norm.norm", True, cast=(1.0, 0.0, 0))
         # 2. attention
-        dy = L.cast_bf16(dres)
         self._wgrad(dy, sv["ctx"], d, d, M, Gv(pre + "attn.linear_out.weight"))
         L.colsum_add(dy, Gv(pre + "attn.linear_out.bias"))
         dctx = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
@@ -375,10 +375,11 @@ class ConformerEngine:
         L.colsum_add(dqkv, Gv(pre + "attn.linear_q.bias", (nq,)))
         dxn = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
         L.gemm(M, d, nq, dqkv, nq, S(pre + "attn.linear_q.weight", self.qkv_w_shape), d, L.EPI_STORE, dxn, d, b_mn=1)
-        gn_bwd(dxn, sv["x1"], sv["st2"], "norm_attn.norm", True)
+        dy = gn_bwd(dxn, sv["x1"], sv["st2"], "norm_attn.norm", True, cast=(0.5, drop, seed + 0 + 1))
         # 1. ff1
-        dxn = self._ff_backward(pre + "ff1.", dres, sv["ff1"], sv["xn1"].view(M, d), M, drop, seed + 0)
-        gn_bwd(dxn, sv["x"], sv["st1"], "norm_ff1.norm", True)
+        dxn = self._ff_backward(pre + "ff1.", dy, sv["ff1"], sv["xn1"].view(M, d), M, drop, seed + 0)
+        # the gradient leaving block 0 feeds input_proj's backward GEMMs: emit its bf16 copy too
+        return gn_bwd(dxn, sv["x"], sv["st1"], "norm_ff1.norm", True, cast=(1.0, 0.0, 0) if i == 0 else None)
 
     def backward(self, tape, dlogits, on_segment_done=None):
         """dlogits (B, T', V) bf16.  Accumulates (+=) every parameter gradient into flat.grads.
@@ -405,12 +406,14 @@ class ConformerEngine:
         L.gemm(M, d, V, dl, dl.stride(0), S("fc.weight"), d, L.EPI_STORE, dres, d, b_mn=1, out_f32=1)
         if on_segment_done is not None:
             on_segment_done(0)
+        dx0 = None
         for k, i in enumerate(reversed(range(self.n_blocks))):
-            self._block_backward(i, dres, tape["blocks"][i], B, T2, tape["key_len"], cs, tape["drop"])
+            dx0 = self._block_backward(i, dres, tape["blocks"][i], B, T2, tape["key_len"], cs, tape["drop"])
             if on_segment_done is not None:
                 on_segment_done(1 + k)
         # input_proj + subsampler (model/conformer.py:177-185)
-        dx0 = L.cast_bf16(dres)
+        if dx0 is None:  # no blocks
+            dx0 = L.cast_bf16(dres)
         y2v = tape["y2"].view(M, F2 * d)
         self._wgrad(dx0, y2v, d, F2 * d, M, Gv("input_proj.weight"), remap=(d, F2))
         L.colsum_add(dx0, Gv("input_proj.bias"))
