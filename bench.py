@@ -33,10 +33,11 @@ UNIT = "audio-s/s"
 
 
 def workload_config(n_gpus):
+    name = "BASELINE configs[1]: default Conformer-CTC" if CFG["d_model"] == 256 else "BASELINE configs[2]: Conformer-M"
     return {
-        "workload": "BASELINE configs[1]: default Conformer-CTC (80 mel, d_model=256, 4 heads, 8 blocks, V=1000) full "
+        "workload": "%s (80 mel, d_model=%d, %d heads, %d blocks, V=1000) full "
                     "training step (log-mel + fwd + CTC + bwd + clip + AdamW), batch 64 bucketed 5-15 s synthetic 16 kHz "
-                    "utterances per GPU, dropout 0.1",
+                    "utterances per GPU, dropout 0.1" % (name, CFG["d_model"], CFG["n_heads"], CFG["n_blocks"]),
         "per_gpu_batch": CFG["batch"], "global_batch": CFG["batch"] * n_gpus, "utterance_seconds": "U[5,15] bucketed",
         "parallelism": "dp%d" % n_gpus,
         "l2": "no explicit flush: every step streams a new batch and >2 GB of activations (>> 126 MB L2)",
@@ -398,7 +399,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--model", default="default", choices=["default", "conformer-m"],
+                    help="default = BASELINE configs[1] (the headline); conformer-m = configs[2] (d_model 512, 8 heads, 16 blocks)")
     args = ap.parse_args()
+    if args.model == "conformer-m":
+        CFG.update(d_model=512, n_heads=8, n_blocks=16)
     if args.impl == "reference":
         run_reference(args)
         return
