@@ -4,6 +4,8 @@
 // Replaces (reference): model/conformer.py:45-49 TransposeGroupNorm.forward (2 transposes +
 //   native_group_norm) and its backward; :84-85 BatchNorm1d + SiLU in ConformerConvModule.
 #include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -360,6 +362,195 @@ __global__ void __launch_bounds__(NT) bn_silu_bwd_apply_kernel(const bf16* __res
   }
 }
 
+// ---------------------------------------------------------------- single-pass GroupNorm on a thread-block cluster
+// One cluster of GN_CL CTAs per utterance: every CTA stages its slice of rows in shared memory while accumulating the
+// per-group sums, the partial sums are exchanged through distributed shared memory, and the rows are normalised
+// straight from shared memory: x is read from global memory exactly once (the two-kernel path reads it twice).
+constexpr int GN_CL = 8;
+
+template <bool OUT_BF16>
+__global__ void __cluster_dims__(GN_CL, 1, 1) __launch_bounds__(NT)
+gn_fused_fwd_kernel(const float* __restrict__ x, int T, int d, int G, int rows_per_cta, float eps,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, void* __restrict__ out,
+                    float* __restrict__ stats_out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float sh_rows[];       // rows_per_cta * d
+  __shared__ float part[64][2];                          // this CTA's per-group (sum, sumsq)
+  __shared__ float sh_s[NT], sh_ss[NT];
+  __shared__ float sh_mean[64], sh_rstd[64];
+  const int b = blockIdx.x / GN_CL, rank = blockIdx.x % GN_CL;
+  const int tpr = d >> 2, rlanes = NT / tpr;
+  const int col = (threadIdx.x % tpr) << 2, rl = threadIdx.x / tpr;
+  const int t0 = rank * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
+  float s = 0.f, ss = 0.f;
+#pragma unroll 4
+  for (int t = t0 + rl; t < t1; t += rlanes) {
+    const float4 v = ld4(x + ((long long)b * T + t) * d + col);
+    *reinterpret_cast<float4*>(sh_rows + (long long)(t - t0) * d + col) = v;
+    s += (v.x + v.y) + (v.z + v.w);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  sh_s[threadIdx.x] = s;
+  sh_ss[threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int tpg = (d / G) >> 2;
+    float a = 0.f, c = 0.f;
+    for (int r = 0; r < rlanes; ++r)
+      for (int j = 0; j < tpg; ++j) {
+        const int idx = r * tpr + threadIdx.x * tpg + j;
+        a += sh_s[idx];
+        c += sh_ss[idx];
+      }
+    part[threadIdx.x][0] = a;
+    part[threadIdx.x][1] = c;
+  }
+  cluster.sync();
+  if (threadIdx.x < G) {
+    double a = 0.0, c = 0.0;
+    for (int r = 0; r < GN_CL; ++r) {
+      const float* rp = cluster.map_shared_rank(&part[0][0], r);
+      a += rp[threadIdx.x * 2];
+      c += rp[threadIdx.x * 2 + 1];
+    }
+    const double n = (double)T * (d / G);
+    const double mean = a / n;
+    double var = c / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    sh_mean[threadIdx.x] = (float)mean;
+    sh_rstd[threadIdx.x] = rstd;
+    if (rank == 0 && stats_out != nullptr) {
+      stats_out[((long long)b * G + threadIdx.x) * 2] = (float)mean;
+      stats_out[((long long)b * G + threadIdx.x) * 2 + 1] = rstd;
+    }
+  }
+  cluster.sync();  // also keeps every CTA's `part` alive until all peers have read it
+  const int g = col / (d / G);
+  const float mean = sh_mean[g], rstd = sh_rstd[g];
+  const float4 ga = ld4(gamma + col), be = ld4(beta + col);
+#pragma unroll 4
+  for (int t = t0 + rl; t < t1; t += rlanes) {
+    float4 v = *reinterpret_cast<const float4*>(sh_rows + (long long)(t - t0) * d + col);
+    v.x = (v.x - mean) * rstd * ga.x + be.x;
+    v.y = (v.y - mean) * rstd * ga.y + be.y;
+    v.z = (v.z - mean) * rstd * ga.z + be.z;
+    v.w = (v.w - mean) * rstd * ga.w + be.w;
+    const long long off = ((long long)b * T + t) * d + col;
+    if (OUT_BF16) st4_bf16(reinterpret_cast<bf16*>(out) + off, v);
+    else *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + off) = v;
+  }
+}
+
+// backward: dx = rstd * (dy*gamma - S1/n - xhat*S2/n); per-channel sums of dy*xhat and dy exchanged through DSMEM
+template <bool DY_BF16>
+__global__ void __cluster_dims__(GN_CL, 1, 1) __launch_bounds__(NT)
+gn_fused_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, int T, int d, int G, int rows_per_cta,
+                    const float* __restrict__ stats, const float* __restrict__ gamma, float* __restrict__ dres,
+                    int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta, bf16* __restrict__ cast_out,
+                    float cast_alpha, uint32_t cast_thresh, float cast_inv_keep, unsigned long long cast_seed,
+                    const unsigned long long* __restrict__ seed_ptr) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float sh_dyn2[];
+  // layout: xhat rows (rows*d f32) | dy rows (rows*d f32) | part a (d) | part c (d) | tot a (d) | tot c (d) | S1 (G) | S2 (G)
+  const int b = blockIdx.x / GN_CL, rank = blockIdx.x % GN_CL;
+  float* sx = sh_dyn2;
+  float* sdy = sx + (long long)rows_per_cta * d;
+  float* pa = sdy + (long long)rows_per_cta * d;
+  float* pc = pa + d;
+  float* ta = pc + d;
+  float* tcx = ta + d;
+  float* s1s = tcx + d;
+  float* s2s = s1s + G;
+  __shared__ float4 red_a[NT], red_c[NT];
+  if (cast_thresh && seed_ptr) cast_seed += *seed_ptr;
+  const int tpr = d >> 2, rlanes = NT / tpr;
+  const int col = (threadIdx.x % tpr) << 2, rl = threadIdx.x / tpr;
+  const int cpg = d / G;
+  const int g = col / cpg;
+  const float mean = stats[((long long)b * G + g) * 2], rstd = stats[((long long)b * G + g) * 2 + 1];
+  const int t0 = rank * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
+  float4 a = make_float4(0, 0, 0, 0), c = make_float4(0, 0, 0, 0);
+#pragma unroll 2
+  for (int t = t0 + rl; t < t1; t += rlanes) {
+    const long long off = ((long long)b * T + t) * d + col;
+    float4 xv = ld4(x + off);
+    const float4 g4 = DY_BF16 ? ld4_bf16(reinterpret_cast<const bf16*>(dy) + off) : ld4(reinterpret_cast<const float*>(dy) + off);
+    xv.x = (xv.x - mean) * rstd; xv.y = (xv.y - mean) * rstd; xv.z = (xv.z - mean) * rstd; xv.w = (xv.w - mean) * rstd;
+    *reinterpret_cast<float4*>(sx + (long long)(t - t0) * d + col) = xv;
+    *reinterpret_cast<float4*>(sdy + (long long)(t - t0) * d + col) = g4;
+    a.x += g4.x * xv.x; a.y += g4.y * xv.y; a.z += g4.z * xv.z; a.w += g4.w * xv.w;
+    c.x += g4.x; c.y += g4.y; c.z += g4.z; c.w += g4.w;
+  }
+  red_a[threadIdx.x] = a;
+  red_c[threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.x < tpr) {
+    for (int r = 1; r < rlanes; ++r) {
+      const float4 a2 = red_a[r * tpr + threadIdx.x], c2 = red_c[r * tpr + threadIdx.x];
+      a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w;
+      c.x += c2.x; c.y += c2.y; c.z += c2.z; c.w += c2.w;
+    }
+    *reinterpret_cast<float4*>(pa + col) = a;
+    *reinterpret_cast<float4*>(pc + col) = c;
+  }
+  cluster.sync();
+  for (int ch = threadIdx.x; ch < d; ch += NT) {
+    float av = 0.f, cv = 0.f;
+    for (int r = 0; r < GN_CL; ++r) {
+      av += cluster.map_shared_rank(pa, r)[ch];
+      cv += cluster.map_shared_rank(pc, r)[ch];
+    }
+    ta[ch] = av;
+    tcx[ch] = cv;
+    if (rank == 0) {
+      if (dgamma) atomicAdd(dgamma + ch, av);
+      if (dbeta) atomicAdd(dbeta + ch, cv);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      const int ch = threadIdx.x * cpg + j;
+      s1 += gamma[ch] * tcx[ch];
+      s2 += gamma[ch] * ta[ch];
+    }
+    const float inv_n = 1.f / ((float)T * cpg);
+    s1s[threadIdx.x] = s1 * inv_n;
+    s2s[threadIdx.x] = s2 * inv_n;
+  }
+  cluster.sync();  // peers have finished reading this CTA's partial sums; S1/S2 visible to the whole CTA
+  const float s1 = s1s[g], s2 = s2s[g];
+  const float4 ga = ld4(gamma + col);
+#pragma unroll 2
+  for (int t = t0 + rl; t < t1; t += rlanes) {
+    const long long off = ((long long)b * T + t) * d + col;
+    const float4 xh = *reinterpret_cast<const float4*>(sx + (long long)(t - t0) * d + col);
+    const float4 g4 = *reinterpret_cast<const float4*>(sdy + (long long)(t - t0) * d + col);
+    float4 r;
+    r.x = rstd * (g4.x * ga.x - s1 - xh.x * s2);
+    r.y = rstd * (g4.y * ga.y - s1 - xh.y * s2);
+    r.z = rstd * (g4.z * ga.z - s1 - xh.z * s2);
+    r.w = rstd * (g4.w * ga.w - s1 - xh.w * s2);
+    if (accumulate) {
+      const float4 o = ld4(dres + off);
+      r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+    }
+    *reinterpret_cast<float4*>(dres + off) = r;
+    if (cast_out != nullptr) {
+      float4 c4 = make_float4(r.x * cast_alpha, r.y * cast_alpha, r.z * cast_alpha, r.w * cast_alpha);
+      if (cast_thresh) {
+        float q0, q1, q2, q3;
+        dropout_scale2(cast_seed, (unsigned long long)off, cast_thresh, cast_inv_keep, q0, q1);
+        dropout_scale2(cast_seed, (unsigned long long)off + 2, cast_thresh, cast_inv_keep, q2, q3);
+        c4.x *= q0; c4.y *= q1; c4.z *= q2; c4.w *= q3;
+      }
+      st4_bf16(cast_out + off, c4);
+    }
+  }
+}
+
 bool gn_shape_ok(int d, int G) {
   if (d <= 0 || G <= 0 || G > 64 || d % G) return false;
   const int cpg = d / G;
@@ -387,6 +578,23 @@ extern "C" int tasr_groupnorm_fwd(const float* x, int B, int T, int d, int G, fl
   if (!gn_shape_ok(d, G) || B <= 0 || T <= 0) return TASR_ERR_SHAPE;
   if (workspace_bytes < tasr_groupnorm_workspace_bytes(B, T, d)) return TASR_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {  // single-pass cluster kernel when one eighth of an utterance fits in shared memory
+    const int frows = cdiv(T, GN_CL);
+    const size_t fsm = (size_t)frows * d * sizeof(float);
+    if (fsm <= 200 * 1024) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaError_t e1 = cudaFuncSetAttribute(gn_fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e2 = cudaFuncSetAttribute(gn_fused_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return tasr_set_cuda_error(e1 != cudaSuccess ? e1 : e2);
+        attr_done = true;
+      }
+      if (out_bf16) gn_fused_fwd_kernel<true><<<B * GN_CL, NT, fsm, st>>>(x, T, d, G, frows, eps, gamma, beta, out, stats);
+      else gn_fused_fwd_kernel<false><<<B * GN_CL, NT, fsm, st>>>(x, T, d, G, frows, eps, gamma, beta, out, stats);
+      TASR_CHECK_LAUNCH();
+      return TASR_OK;
+    }
+  }
   const int rows = gn_rows_per_cta(B, T), nchunk = cdiv(T, rows);
   float* partial = reinterpret_cast<float*>(workspace);
   dim3 grid(nchunk, B);
@@ -408,6 +616,27 @@ extern "C" int tasr_groupnorm_bwd(const void* dy, int dy_bf16, const float* x, i
   if (!gn_shape_ok(d, G) || B <= 0 || T <= 0) return TASR_ERR_SHAPE;
   if (workspace_bytes < tasr_groupnorm_workspace_bytes(B, T, d)) return TASR_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    const int frows = cdiv(T, GN_CL);
+    const size_t fsm = ((size_t)2 * frows * d + 4 * d + 2 * G) * sizeof(float);
+    if (fsm <= 190 * 1024) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaError_t e1 = cudaFuncSetAttribute(gn_fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);
+        cudaError_t e2 = cudaFuncSetAttribute(gn_fused_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return tasr_set_cuda_error(e1 != cudaSuccess ? e1 : e2);
+        attr_done = true;
+      }
+      if (dy_bf16)
+        gn_fused_bwd_kernel<true><<<B * GN_CL, NT, fsm, st>>>(dy, x, T, d, G, frows, stats, gamma, dres, accumulate, dgamma, dbeta,
+                                                             cout_, cast_alpha, cthresh, cinv, cast_seed, g_tasr_seed_ptr);
+      else
+        gn_fused_bwd_kernel<false><<<B * GN_CL, NT, fsm, st>>>(dy, x, T, d, G, frows, stats, gamma, dres, accumulate, dgamma, dbeta,
+                                                              cout_, cast_alpha, cthresh, cinv, cast_seed, g_tasr_seed_ptr);
+      TASR_CHECK_LAUNCH();
+      return TASR_OK;
+    }
+  }
   const int rows = gn_rows_per_cta(B, T), nchunk = cdiv(T, rows);
   float* partial = reinterpret_cast<float*>(workspace);
   dim3 grid(nchunk, B);
