@@ -305,8 +305,14 @@ def rope_inplace(qkv, T, rot_cols, cos_sin, inverse=False):
 # ---------------------------------------------------------------------------------------------
 # attention
 # ---------------------------------------------------------------------------------------------
+def _check_key_lengths(key_lengths, B):
+    if key_lengths is not None and (key_lengths.dtype != torch.int64 or key_lengths.numel() != B or not key_lengths.is_cuda):
+        raise ValueError("key_lengths must be a CUDA int64 tensor of B elements")
+
+
 def mqa_fwd(qkv, B, T, H, d, key_lengths, drop_p=0.0, seed=0):
     require_cuda(qkv)
+    _check_key_lengths(key_lengths, B)
     ctx = torch.empty(B * T, d, dtype=torch.bfloat16, device=qkv.device)
     lse2 = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
     check(lib().tasr_mqa_attention_fwd(ptr(qkv), B, T, H, d, ptr(key_lengths), drop_p, seed, ptr(ctx), ptr(lse2),
@@ -315,6 +321,7 @@ def mqa_fwd(qkv, B, T, H, d, key_lengths, drop_p=0.0, seed=0):
 
 
 def mqa_bwd(qkv, ctx, dctx, lse2, B, T, H, d, key_lengths, cos_sin, drop_p=0.0, seed=0):
+    _check_key_lengths(key_lengths, B)
     dqkv = torch.empty_like(qkv)
     wsb = lib().tasr_mqa_attention_bwd_workspace_bytes(B, T, H, d)
     ws = workspace(wsb, qkv.device)

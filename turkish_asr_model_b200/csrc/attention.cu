@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(ATT_THREADS) mqa_fwd_kernel(const __grid_const
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
-  const int Lk = p.key_len ? (int)min((long long)p.T, p.key_len[b]) : p.T;
+  const int Lk = p.key_len ? (int)max(0LL, min((long long)p.T, p.key_len[b])) : p.T;
   const int nkv = (Lk + BKV - 1) / BKV;
 
   if (tid == 0) {
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS) mqa_bwd_kernel(const __grid_c
   const int rloc = quarter * 32 + lane;  // TMEM lane = row of the tile
   const int j = blockIdx.x, b = blockIdx.y;
   const int k0 = j * BKV;
-  const int Lk = p.key_len ? (int)min((long long)p.T, p.key_len[b]) : p.T;
+  const int Lk = p.key_len ? (int)max(0LL, min((long long)p.T, p.key_len[b])) : p.T;
   const int ld = p.d + 2 * DH;
   const int krow = k0 + rloc;
 

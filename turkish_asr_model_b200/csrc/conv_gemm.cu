@@ -283,180 +283,260 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv1 (1 -> d channels, K = 9): direct, bandwidth bound.  One 8-channel slice per thread.
+// conv1 (1 -> d channels, K = 9): direct on the CUDA cores (issue bound, not HBM bound: 9 FMA + SiLU per output).
+// Work item = one output row segment of PX columns x (32 lanes x CH channels); a warp walks items on its own (no CTA
+// barrier in the loop, so the FMA / MUFU / store phases of different warps overlap).  The 3 x (2 PX + 1) input patch of
+// an item is staged by the warp in its private shared-memory slot, every value stored twice (x, x) so one LDS.64 feeds
+// the packed fp32x2 FMAs (FFMA2 on channel pairs); the next item's patch is in flight while this one is computed.
+// SiLU uses one MUFU.TANH: silu(z) = h + h tanh(h), h = z / 2.
 // ------------------------------------------------------------------------------------------------
 constexpr int NT = 256;
+constexpr int NWARP = NT / 32;
+constexpr int PX = 5;               // output columns per item (F1 = 40 -> 8 items per row)
+constexpr int PCOLS = 2 * PX + 1;   // 11 patch columns; 3 x 11 = 33 patch values: lane l stages value l, lane 0 also value 32
+constexpr int PSLOT = 3 * (PCOLS + 1);
 
-__device__ __forceinline__ void conv1_point(const float* __restrict__ xb, int T, int F, int h, int w,
-                                            const float* __restrict__ w1s, const float* __restrict__ b1s, int d, int c0,
-                                            float* z, float* xin) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int tt = 2 * h - 1 + i, ff = 2 * w - 1 + j;
-      xin[i * 3 + j] = (tt >= 0 && tt < T && ff >= 0 && ff < F) ? xb[(long long)tt * F + ff] : 0.f;
-    }
-#pragma unroll
-  for (int q = 0; q < 8; ++q) z[q] = b1s[c0 + q];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const float4 wa = *reinterpret_cast<const float4*>(w1s + k * d + c0);
-    const float4 wb = *reinterpret_cast<const float4*>(w1s + k * d + c0 + 4);
-    const float xv = xin[k];
-    z[0] = fmaf(xv, wa.x, z[0]); z[1] = fmaf(xv, wa.y, z[1]); z[2] = fmaf(xv, wa.z, z[2]); z[3] = fmaf(xv, wa.w, z[3]);
-    z[4] = fmaf(xv, wb.x, z[4]); z[5] = fmaf(xv, wb.y, z[5]); z[6] = fmaf(xv, wb.z, z[6]); z[7] = fmaf(xv, wb.w, z[7]);
-  }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-// Each thread: 8 channels x PX = 4 neighbouring output columns of one row (the 3 x 9 input patch and the 72
-// weights are loaded once for 32 outputs).
-constexpr int PX = 4;
+// A warp keeps one (column group, channel slice) for the whole kernel and walks output rows with a fixed stride, so the
+// per-item index arithmetic is a handful of adds (no divisions), and the backward's accumulators stay on one slice.
+struct WarpWalk {
+  int w0, c0, npx;         // first output column, first channel of this lane, valid columns (<= PX)
+  int row, rstep, nrows;   // current output row (b * T1 + h), stride, B * T1
+  bool active;
+  // patch staging (lane l stages patch value l = (r0, j0); lane 0 also value 32 = (2, PCOLS - 1))
+  int r0, j0, ff0, ff1, pb, ph;
+  bool colok0, colok1;
+  float v0, v1;
+  int T, F, T1;
+  const float* x;
 
-__device__ __forceinline__ void load_patch(const float* __restrict__ xb, int T, int F, int h, int w0, float (*xp)[2 * PX + 1]) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int tt = 2 * h - 1 + i;
-    const bool rok = tt >= 0 && tt < T;
-#pragma unroll
-    for (int j = 0; j < 2 * PX + 1; ++j) {
-      const int ff = 2 * w0 - 1 + j;
-      xp[i][j] = (rok && ff >= 0 && ff < F) ? xb[(long long)tt * F + ff] : 0.f;
+  __device__ __forceinline__ void init(const float* x_, int B, int T_, int F_, int T1_, int F1, int d, int chw) {
+    const int lane = threadIdx.x & 31;
+    x = x_; T = T_; F = F_; T1 = T1_;
+    nrows = B * T1;
+    const int wgroups = (F1 + PX - 1) / PX, nch = (d + chw - 1) / chw;
+    const int slices = wgroups * nch;
+    const int nwarps = gridDim.x * NWARP;
+    const int used = (nwarps / slices) * slices;
+    const int gw = blockIdx.x * NWARP + (threadIdx.x >> 5);
+    active = gw < used;
+    const int slice = gw % slices;
+    w0 = (slice / nch) * PX;
+    c0 = (slice % nch) * chw + lane * (chw / 32);
+    npx = min(PX, F1 - w0);
+    row = gw / slices;
+    rstep = used / slices;
+    r0 = lane / PCOLS;
+    j0 = lane - r0 * PCOLS;
+    ff0 = 2 * w0 - 1 + j0;
+    ff1 = 2 * w0 - 1 + PCOLS - 1;
+    colok0 = ff0 >= 0 && ff0 < F;
+    colok1 = lane == 0 && ff1 < F;
+    pb = row / T1;
+    ph = row - pb * T1;
+  }
+  // loads the patch of the row (pb, ph) and advances (pb, ph) by rstep rows
+  __device__ __forceinline__ void prefetch(bool valid) {
+    v0 = v1 = 0.f;
+    if (valid) {
+      const int tt0 = 2 * ph - 1 + r0, tt1 = 2 * ph + 1;
+      const float* xb = x + (long long)pb * T * F;
+      if (colok0 && tt0 >= 0 && tt0 < T) v0 = xb[tt0 * F + ff0];
+      if (colok1 && tt1 < T) v1 = xb[tt1 * F + ff1];
+    }
+    ph += rstep;
+    while (ph >= T1) {
+      ph -= T1;
+      ++pb;
     }
   }
-}
-__device__ __forceinline__ void conv1_rows(const float (*xp)[2 * PX + 1], const float* __restrict__ w1s,
-                                           const float* __restrict__ b1s, int d, int c0, float (*z)[8]) {
-#pragma unroll
-  for (int px = 0; px < PX; ++px)
-#pragma unroll
-    for (int q = 0; q < 8; ++q) z[px][q] = b1s[c0 + q];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const float4 wa = *reinterpret_cast<const float4*>(w1s + k * d + c0);
-    const float4 wb = *reinterpret_cast<const float4*>(w1s + k * d + c0 + 4);
-    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-    for (int px = 0; px < PX; ++px) {
-      const float xv = xp[k / 3][2 * px + k % 3];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) z[px][q] = fmaf(xv, wv[q], z[px][q]);
-    }
+  __device__ __forceinline__ void commit(float2* __restrict__ slot) const {
+    slot[r0 * (PCOLS + 1) + j0] = make_float2(v0, v0);
+    if ((threadIdx.x & 31) == 0) slot[2 * (PCOLS + 1) + PCOLS - 1] = make_float2(v1, v1);
+    __syncwarp();
   }
-}
+};
 
-// x (B, T, F) fp32 -> y1 (B, T1, F1, d) bf16 = silu(conv1(x))
-__global__ void __launch_bounds__(NT) conv1_fwd_kernel(const float* __restrict__ x, int B, int T, int F, int d,
-                                                       const float* __restrict__ w1, const float* __restrict__ b1, int T1,
-                                                       int F1, bf16* __restrict__ y1) {
-  extern __shared__ float sh_w[];
-  float* w1s = sh_w;
-  float* b1s = sh_w + 9 * d;
-  for (int i = threadIdx.x; i < 9 * d; i += NT) {
-    const int k = i / d, c = i - k * d;
-    w1s[i] = w1[c * 9 + k];
-  }
-  for (int i = threadIdx.x; i < d; i += NT) b1s[i] = b1[i];
-  __syncthreads();
-  const int lanes_per_item = d >> 3;
-  const int items_per_iter = NT / lanes_per_item;
-  const int c0 = (threadIdx.x % lanes_per_item) << 3;
-  const int sub = threadIdx.x / lanes_per_item;
-  const int wgroups = (F1 + PX - 1) / PX;
-  const long long total = (long long)B * T1 * wgroups;
-  for (long long item = (long long)blockIdx.x * items_per_iter + sub; item < total; item += (long long)gridDim.x * items_per_iter) {
-    const int wg = (int)(item % wgroups);
-    const long long bh = item / wgroups;
-    const int h = (int)(bh % T1), b = (int)(bh / T1);
-    const int w0 = wg * PX;
-    float xp[3][2 * PX + 1], z[PX][8];
-    load_patch(x + (long long)b * T * F, T, F, h, w0, xp);
-    conv1_rows(xp, w1s, b1s, d, c0, z);
+// z[px][q2] (channel pairs) = b1 + sum_k patch[k of px] * w1[k]
+template <int CH>
+__device__ __forceinline__ void conv1_cols(const float2* __restrict__ patch, const float* __restrict__ w1s,
+                                           const float* __restrict__ b1s, int d, int c0, float2 (*z)[CH / 2]) {
 #pragma unroll
-    for (int px = 0; px < PX; ++px) {
-      if (w0 + px < F1) {
-        uint4 o;
-        o.x = pack_bf16x2(siluf_(z[px][0]), siluf_(z[px][1]));
-        o.y = pack_bf16x2(siluf_(z[px][2]), siluf_(z[px][3]));
-        o.z = pack_bf16x2(siluf_(z[px][4]), siluf_(z[px][5]));
-        o.w = pack_bf16x2(siluf_(z[px][6]), siluf_(z[px][7]));
-        *reinterpret_cast<uint4*>(y1 + (((long long)b * T1 + h) * F1 + w0 + px) * d + c0) = o;
+  for (int q = 0; q < CH / 2; ++q) {
+    const float2 bv = *reinterpret_cast<const float2*>(b1s + c0 + 2 * q);
+#pragma unroll
+    for (int px = 0; px < PX; ++px) z[px][q] = bv;
+  }
+#pragma unroll 1
+  for (int kh = 0; kh < 3; ++kh) {  // not unrolled: keeps only one kernel row of weights (3 x CH) live
+    const float2* xrow = patch + kh * (PCOLS + 1);
+    const float* wrow = w1s + kh * 3 * d + c0;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      float2 wv[CH / 2];
+#pragma unroll
+      for (int q = 0; q < CH / 4; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wrow + kw * d + 4 * q);
+        wv[2 * q] = make_float2(w4.x, w4.y);
+        wv[2 * q + 1] = make_float2(w4.z, w4.w);
+      }
+#pragma unroll
+      for (int px = 0; px < PX; ++px) {
+        const float2 xx = xrow[2 * px + kw];
+#pragma unroll
+        for (int q = 0; q < CH / 2; ++q) z[px][q] = __ffma2_rn(xx, wv[q], z[px][q]);
       }
     }
   }
 }
 
-// dy1 (B, T1, F1, d) bf16 -> dW1 (d,1,3,3), db1 (d)  (+=);  z1 is recomputed from x
-__global__ void __launch_bounds__(NT) conv1_bwd_kernel(const bf16* __restrict__ dy1, const float* __restrict__ x, int B,
-                                                       int T, int F, int d, const float* __restrict__ w1,
-                                                       const float* __restrict__ b1, int T1, int F1, float* __restrict__ dw1,
-                                                       float* __restrict__ db1) {
-  extern __shared__ float sh_w[];
-  float* w1s = sh_w;
-  float* b1s = sh_w + 9 * d;
-  float* red = b1s + d;
-  for (int i = threadIdx.x; i < 9 * d; i += NT) {
-    const int k = i / d, c = i - k * d;
-    w1s[i] = w1[c * 9 + k];
+__device__ __forceinline__ void stage_conv1_weights(float* w1s, float* b1s, const float* __restrict__ w1,
+                                                    const float* __restrict__ b1, int d, int dpad) {
+  for (int i = threadIdx.x; i < 9 * dpad; i += NT) {
+    const int k = i / dpad, c = i - k * dpad;
+    w1s[i] = c < d ? w1[c * 9 + k] : 0.f;
   }
-  for (int i = threadIdx.x; i < d; i += NT) b1s[i] = b1[i];
-  for (int i = threadIdx.x; i < 10 * d; i += NT) red[i] = 0.f;
+  for (int i = threadIdx.x; i < dpad; i += NT) b1s[i] = i < d ? b1[i] : 0.f;
+}
+
+// silu on a channel pair: h + h tanh(h), h = z / 2  (packed FMUL2 / FFMA2 around two MUFU.TANH)
+__device__ __forceinline__ uint32_t silu_pack(float2 z) {
+  const float2 h = __fmul2_rn(z, make_float2(0.5f, 0.5f));
+  const float2 t = make_float2(tanh_approx(h.x), tanh_approx(h.y));
+  const float2 o = __ffma2_rn(h, t, h);
+  return pack_bf16x2(o.x, o.y);
+}
+
+// x (B, T, F) fp32 -> y1 (B, T1, F1, d) bf16 = silu(conv1(x));  8 channels x PX columns per thread
+__global__ void __launch_bounds__(NT, 2) conv1_fwd_kernel(const float* __restrict__ x, int B, int T, int F, int d, int dpad,
+                                                          const float* __restrict__ w1, const float* __restrict__ b1, int T1,
+                                                          int F1, bf16* __restrict__ y1) {
+  extern __shared__ __align__(16) float sh_w[];
+  float* w1s = sh_w;                 // [9][dpad]
+  float* b1s = sh_w + 9 * dpad;      // [dpad]
+  float2* slots = reinterpret_cast<float2*>(b1s + dpad) + (threadIdx.x >> 5) * 2 * PSLOT;  // per warp [2][PSLOT]
+  stage_conv1_weights(w1s, b1s, w1, b1, d, dpad);
   __syncthreads();
-  const int lanes_per_item = d >> 3;
-  const int items_per_iter = NT / lanes_per_item;
-  const int c0 = (threadIdx.x % lanes_per_item) << 3;
-  const int sub = threadIdx.x / lanes_per_item;
-  float gw[9][8];
-  float gb[8];
+  WarpWalk wk;
+  wk.init(x, B, T, F, T1, F1, d, 256);
+  if (!wk.active) return;
+  wk.prefetch(wk.row < wk.nrows);
+  wk.commit(slots);
+  bf16* yp = y1 + ((long long)wk.row * F1 + wk.w0) * d + wk.c0;
+  const long long ystep = (long long)wk.rstep * F1 * d;
+  const bool cok = wk.c0 < d;
+  int buf = 0;
+  for (int row = wk.row; row < wk.nrows; row += wk.rstep, buf ^= 1, yp += ystep) {
+    wk.prefetch(row + wk.rstep < wk.nrows);
+    float2 z[PX][4];
+    conv1_cols<8>(slots + buf * PSLOT, w1s, b1s, dpad, wk.c0, z);
+    if (cok) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    gb[q] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) gw[k][q] = 0.f;
+      for (int px = 0; px < PX; ++px) {
+        if (px < wk.npx) {
+          uint4 o;
+          o.x = silu_pack(z[px][0]);
+          o.y = silu_pack(z[px][1]);
+          o.z = silu_pack(z[px][2]);
+          o.w = silu_pack(z[px][3]);
+          *reinterpret_cast<uint4*>(yp + (long long)px * d) = o;
+        }
+      }
+    }
+    wk.commit(slots + (buf ^ 1) * PSLOT);
   }
-  const int wgroups = (F1 + PX - 1) / PX;
-  const long long total = (long long)B * T1 * wgroups;
-  for (long long item = (long long)blockIdx.x * items_per_iter + sub; item < total; item += (long long)gridDim.x * items_per_iter) {
-    const int wg = (int)(item % wgroups);
-    const long long bh = item / wgroups;
-    const int h = (int)(bh % T1), b = (int)(bh / T1);
-    const int w0 = wg * PX;
-    uint4 u[PX];
+}
+
+// dy1 (B, T1, F1, d) bf16 -> dW1 (d,1,3,3), db1 (d)  (+=);  z1 is recomputed from x.  4 channels x PX columns per thread
+// (36 + 4 gradient accumulators in registers for the whole kernel) so that two CTAs fit an SM.
+__global__ void __launch_bounds__(NT, 2) conv1_bwd_kernel(const bf16* __restrict__ dy1, const float* __restrict__ x, int B,
+                                                          int T, int F, int d, int dpad, const float* __restrict__ w1,
+                                                          const float* __restrict__ b1, int T1, int F1, float* __restrict__ dw1,
+                                                          float* __restrict__ db1) {
+  extern __shared__ __align__(16) float sh_w[];
+  float* w1s = sh_w;
+  float* b1s = sh_w + 9 * dpad;
+  float* red = b1s + dpad;  // [10][dpad]
+  float2* slots = reinterpret_cast<float2*>(red + 10 * dpad) + (threadIdx.x >> 5) * 2 * PSLOT;
+  stage_conv1_weights(w1s, b1s, w1, b1, d, dpad);
+  for (int i = threadIdx.x; i < 10 * dpad; i += NT) red[i] = 0.f;
+  __syncthreads();
+  WarpWalk wk;
+  wk.init(x, B, T, F, T1, F1, d, 128);
+  const int c0 = wk.c0;
+  const bool cok = c0 < d;
+  if (wk.active) {
+    float2 gw[9][2], gb[2];
 #pragma unroll
-    for (int px = 0; px < PX; ++px)
-      u[px] = (w0 + px < F1) ? *reinterpret_cast<const uint4*>(dy1 + (((long long)b * T1 + h) * F1 + w0 + px) * d + c0)
-                             : make_uint4(0, 0, 0, 0);
-    float xp[3][2 * PX + 1], z[PX][8];
-    load_patch(x + (long long)b * T * F, T, F, h, w0, xp);
-    conv1_rows(xp, w1s, b1s, d, c0, z);
+    for (int q = 0; q < 2; ++q) {
+      gb[q] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int px = 0; px < PX; ++px) {
-      float g[8];
-      float2 t;
-      t = unpack_bf16x2(u[px].x); g[0] = t.x; g[1] = t.y;
-      t = unpack_bf16x2(u[px].y); g[2] = t.x; g[3] = t.y;
-      t = unpack_bf16x2(u[px].z); g[4] = t.x; g[5] = t.y;
-      t = unpack_bf16x2(u[px].w); g[6] = t.x; g[7] = t.y;
+      for (int k = 0; k < 9; ++k) gw[k][q] = make_float2(0.f, 0.f);
+    }
+    wk.prefetch(wk.row < wk.nrows);
+    wk.commit(slots);
+    const bf16* gp = dy1 + ((long long)wk.row * F1 + wk.w0) * d + c0;
+    const long long gstep = (long long)wk.rstep * F1 * d;
+    const float2 half2 = make_float2(0.5f, 0.5f), one2 = make_float2(1.f, 1.f), mone2 = make_float2(-1.f, -1.f);
+    int buf = 0;
+    for (int row = wk.row; row < wk.nrows; row += wk.rstep, buf ^= 1, gp += gstep) {
+      wk.prefetch(row + wk.rstep < wk.nrows);
+      const float2* patch = slots + buf * PSLOT;
+      uint2 u[PX];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float dz = g[q] * silu_gradf_(z[px][q]);
-        gb[q] += dz;
+      for (int px = 0; px < PX; ++px)
+        u[px] = (cok && px < wk.npx) ? *reinterpret_cast<const uint2*>(gp + (long long)px * d) : make_uint2(0, 0);
+      float2 z[PX][2];
+      conv1_cols<4>(patch, w1s, b1s, dpad, c0, z);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) gw[k][q] = fmaf(dz, xp[k / 3][2 * px + k % 3], gw[k][q]);
+      for (int px = 0; px < PX; ++px) {
+        const uint32_t uu[2] = {u[px].x, u[px].y};
+        float2 dz[2];  // 2 x dz: silu'(z) = (1 + t)(1 + h (1 - t)) / 2 with h = z / 2, t = tanh(h); the 1/2 is applied at the end
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float2 g = unpack_bf16x2(uu[q]);
+          const float2 h = __fmul2_rn(z[px][q], half2);
+          const float2 t = make_float2(tanh_approx(h.x), tanh_approx(h.y));
+          const float2 a1 = __fadd2_rn(t, one2);
+          const float2 b1m = __ffma2_rn(t, mone2, one2);
+          const float2 c = __ffma2_rn(h, b1m, one2);
+          dz[q] = __fmul2_rn(g, __fmul2_rn(a1, c));
+          gb[q] = __fadd2_rn(gb[q], dz[q]);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float2 xx = patch[(k / 3) * (PCOLS + 1) + 2 * px + (k % 3)];
+          gw[k][0] = __ffma2_rn(dz[0], xx, gw[k][0]);
+          gw[k][1] = __ffma2_rn(dz[1], xx, gw[k][1]);
+        }
+      }
+      wk.commit(slots + (buf ^ 1) * PSLOT);
+    }
+    if (cok) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          atomicAdd(&red[k * dpad + c0 + 2 * q], 0.5f * gw[k][q].x);
+          atomicAdd(&red[k * dpad + c0 + 2 * q + 1], 0.5f * gw[k][q].y);
+        }
+        atomicAdd(&red[9 * dpad + c0 + 2 * q], 0.5f * gb[q].x);
+        atomicAdd(&red[9 * dpad + c0 + 2 * q + 1], 0.5f * gb[q].y);
       }
     }
   }
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) atomicAdd(&red[k * d + c0 + q], gw[k][q]);
-    atomicAdd(&red[9 * d + c0 + q], gb[q]);
-  }
   __syncthreads();
-  for (int i = threadIdx.x; i < 10 * d; i += NT) {
-    const int k = i / d, c = i - k * d;
-    if (k < 9) atomicAdd(dw1 + c * 9 + k, red[i]);
-    else atomicAdd(db1 + c, red[i]);
+  for (int i = threadIdx.x; i < 10 * dpad; i += NT) {
+    const int k = i / dpad, c = i - k * dpad;
+    if (c < d) {
+      if (k < 9) atomicAdd(dw1 + c * 9 + k, red[i]);
+      else atomicAdd(db1 + c, red[i]);
+    }
   }
 }
 
@@ -568,26 +648,46 @@ bool conv_shape_ok(int B, int T, int F, int d) {
 
 extern "C" int tasr_conv1_fwd(const float* x, int B, int T, int F, int d, const float* w1, const float* b1, void* y1,
                               tasr_stream_t stream) {
-  if (d % 8 || d > 2048 || (NT % (d / 8)) || B <= 0 || T <= 0 || F <= 0) return TASR_ERR_SHAPE;
+  if (d % 8 || d > 1024 || B <= 0 || T <= 0 || F <= 0) return TASR_ERR_SHAPE;
   Geom g = geom(T, F);
-  const long long total = (long long)B * g.T1 * ((g.F1 + PX - 1) / PX);
-  const int per = NT / (d / 8);
-  const int grid = (int)imin64((long long)148 * 8, (total + per - 1) / per);
-  conv1_fwd_kernel<<<grid, NT, (size_t)10 * d * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, B, T, F, d, w1, b1, g.T1, g.F1, reinterpret_cast<bf16*>(y1));
+  const int dpad = cdiv(d, 256) * 256;
+  const int slices = cdiv(g.F1, PX) * (dpad / 256);
+  const long long total = (long long)B * g.T1 * slices;
+  if (total > 0x3fffffffLL || (long long)T * F > 0x3fffffffLL) return TASR_ERR_SHAPE;
+  int grid = (int)imin64(cdiv(total, NWARP), 2 * g_sms);
+  if (grid * NWARP < slices) grid = cdiv(slices, NWARP);
+  const size_t smem = ((size_t)10 * dpad + NWARP * 2 * PSLOT * 2) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return tasr_set_cuda_error(e);
+    attr_done = true;
+  }
+  conv1_fwd_kernel<<<grid, NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, B, T, F, d, dpad, w1, b1, g.T1, g.F1,
+                                                                              reinterpret_cast<bf16*>(y1));
   TASR_CHECK_LAUNCH();
   return TASR_OK;
 }
 
 extern "C" int tasr_conv1_bwd(const void* dy1, const float* x, int B, int T, int F, int d, const float* w1, const float* b1,
                               float* dw1, float* db1, tasr_stream_t stream) {
-  if (d % 8 || d > 1024 || (NT % (d / 8)) || B <= 0 || T <= 0 || F <= 0) return TASR_ERR_SHAPE;
+  if (d % 8 || d > 1024 || B <= 0 || T <= 0 || F <= 0) return TASR_ERR_SHAPE;
   Geom g = geom(T, F);
-  const long long total = (long long)B * g.T1 * ((g.F1 + PX - 1) / PX);
-  const int per = NT / (d / 8);
-  const int grid = (int)imin64((long long)148 * 4, (total + per - 1) / per);
-  conv1_bwd_kernel<<<grid, NT, (size_t)20 * d * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(dy1), x, B, T, F, d, w1, b1, g.T1, g.F1, dw1, db1);
+  const int dpad = cdiv(d, 128) * 128;
+  const int slices = cdiv(g.F1, PX) * (dpad / 128);
+  const long long total = (long long)B * g.T1 * slices;
+  if (total > 0x3fffffffLL || (long long)T * F > 0x3fffffffLL) return TASR_ERR_SHAPE;
+  int grid = (int)imin64(cdiv(total, NWARP), 2 * g_sms);
+  if (grid * NWARP < slices) grid = cdiv(slices, NWARP);
+  const size_t smem = ((size_t)20 * dpad + NWARP * 2 * PSLOT * 2) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return tasr_set_cuda_error(e);
+    attr_done = true;
+  }
+  conv1_bwd_kernel<<<grid, NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(dy1), x, B, T, F, d,
+                                                                              dpad, w1, b1, g.T1, g.F1, dw1, db1);
   TASR_CHECK_LAUNCH();
   return TASR_OK;
 }
