@@ -17,7 +17,7 @@ namespace {
 constexpr int DH = 64;
 constexpr int BQ = 128;   // query rows per tile
 constexpr int BKV = 128;  // keys per block
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_THREADS = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnParams {
@@ -58,26 +58,38 @@ __device__ __forceinline__ unsigned long long drop_index(int b, int h, int H, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward: grid (ceil(T/128), H, B)
+// forward: grid (ceil(T/128), H, B), 256 threads.  Two threads share a query row (= TMEM lane): warps 0-3 own key
+// columns [0,64) of every 128-key S tile and columns [0,32) of O, warps 4-7 the other halves; the block row-max and
+// the final row sum are exchanged through shared memory.  K(j+1) is fetched while block j is in the softmax, V(j+1)
+// while S(j+1) is computed.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ATT_THREADS) mqa_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) {
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2) mqa_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;            // 16 KB
   uint8_t* sK = smem + 16384;    // 16 KB
   uint8_t* sV = smem + 32768;    // 16 KB
   uint8_t* sP = smem + 49152;    // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);  // q, kv, s, o
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);  // q, k, v, s, o
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* xch = reinterpret_cast<float*>(smem + 81920 + 64);    // [2][128]
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int rloc = quarter * 32 + lane;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int Lk = p.key_len ? (int)max(0LL, min((long long)p.T, p.key_len[b])) : p.T;
   const int nkv = (Lk + BKV - 1) / BKV;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 256);
@@ -87,30 +99,39 @@ __global__ void __launch_bounds__(ATT_THREADS) mqa_fwd_kernel(const __grid_const
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tO = tmem + 128;
 
-  if (tid == 0) {
+  auto load_k = [&](int j) {
+    mbar_expect_tx(&bars[1], 16384);
+    tma_load_3d(sK, &tm_qkv, &bars[1], p.d, j * BKV, b);
+    tma_load_3d(sK + 8192, &tm_qkv, &bars[1], p.d, j * BKV + 64, b);
+  };
+  auto load_v = [&](int j) {
+    mbar_expect_tx(&bars[2], 16384);
+    tma_load_3d(sV, &tm_qkv, &bars[2], p.d + DH, j * BKV, b);
+    tma_load_3d(sV + 8192, &tm_qkv, &bars[2], p.d + DH, j * BKV + 64, b);
+  };
+  if (tid == 0 && nkv > 0) {
     mbar_expect_tx(&bars[0], 16384);
     tma_load_3d(sQ, &tm_qkv, &bars[0], h * DH, q0, b);
     tma_load_3d(sQ + 8192, &tm_qkv, &bars[0], h * DH, q0 + 64, b);
+    load_k(0);
+    load_v(0);
   }
   const unsigned long long dseed = (p.drop_thresh && p.seed_ptr) ? p.seed + *p.seed_ptr : p.seed;
   const float scale2 = p.scale * LOG2E;
-  float m_run = -INFINITY, l_run = 0.f;
-  float o[DH];
+  float m_run = -INFINITY, l_part = 0.f;
+  float o[32];
 #pragma unroll
-  for (int i = 0; i < DH; ++i) o[i] = 0.f;
-  const int qrow = q0 + tid;
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  for (int i = 0; i < 32; ++i) o[i] = 0.f;
+  const int qrow = q0 + rloc;
+  const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
+  const int Tp = (p.T + 1) & ~1;  // even row pitch of the dropout index space
+  const unsigned long long drow = ((unsigned long long)(b * p.H + h) * p.T + qrow) * (unsigned long long)Tp;
 
   for (int j = 0; j < nkv; ++j) {
     const uint32_t ph = (uint32_t)j & 1u;
     if (tid == 0) {
-      mbar_expect_tx(&bars[1], 32768);
-      tma_load_3d(sK, &tm_qkv, &bars[1], p.d, j * BKV, b);
-      tma_load_3d(sK + 8192, &tm_qkv, &bars[1], p.d, j * BKV + 64, b);
-      tma_load_3d(sV, &tm_qkv, &bars[1], p.d + DH, j * BKV, b);
-      tma_load_3d(sV + 8192, &tm_qkv, &bars[1], p.d + DH, j * BKV + 64, b);
       if (j == 0) mbar_wait(&bars[0], 0);
       mbar_wait(&bars[1], ph);
       tc_fence_after();
@@ -118,81 +139,103 @@ __global__ void __launch_bounds__(ATT_THREADS) mqa_fwd_kernel(const __grid_const
 #pragma unroll
       for (int k = 0; k < DH / 16; ++k)
         umma_bf16(tS, umma_desc_sw128(qa + k * 32, 16, 1024), umma_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
-      umma_commit(&bars[2]);
+      umma_commit(&bars[3]);
     }
-    mbar_wait(&bars[2], ph);
+    mbar_wait(&bars[3], ph);
     __syncwarp();
     tc_fence_after();
-    // pass 1: block row max
+    if (tid == 0 && j + 1 < nkv) load_k(j + 1);  // S(j) is complete: the K tile is free
+    const int nvalid = Lk - j * BKV;             // keys of this block that exist (>= 1)
+    const bool tail = nvalid < BKV;
+    // pass 1: row max over this thread's 64 columns
     float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < BKV / 32; ++c) {
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = half * 2 + cc;
       uint32_t u[32];
       tmem_ld32(tS + lane_addr + c * 32, u);
       tmem_ld_wait();
+      if (!tail) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int key = j * BKV + c * 32 + i;
-        const float s = __uint_as_float(u[i]) * scale2;
-        if (key < Lk) mx = fmaxf(mx, s);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(u[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(u[i]));
       }
     }
+    xch[half * 128 + rloc] = mx;
+    __syncthreads();
+    mx = fmaxf(mx, xch[(half ^ 1) * 128 + rloc]) * scale2;  // scale2 > 0; at least one valid key per block
     const float m_new = fmaxf(m_run, mx);
-    const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+    const float corr = fast_exp2(m_run - m_new);  // 0 on the first block (m_run = -inf)
     float lsum = 0.f;
-    // pass 2: probabilities -> shared memory (bf16)
-#pragma unroll 1
-    for (int c = 0; c < BKV / 32; ++c) {
+    // pass 2: probabilities -> shared memory (bf16, A operand of the PV product)
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = half * 2 + cc;
       uint32_t u[32];
       tmem_ld32(tS + lane_addr + c * 32, u);
       tmem_ld_wait();
       float pv[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int key = j * BKV + c * 32 + i;
-        float e = 0.f;
-        if (key < Lk) e = exp2f(__uint_as_float(u[i]) * scale2 - m_new);
-        lsum += e;
-        if (p.drop_thresh) e *= dropout_scale(dseed, drop_index(b, h, p.H, p.T, qrow, key), p.drop_thresh, p.drop_inv_keep);
-        pv[i] = e;
+      for (int i = 0; i < 32; i += 2) {
+        float e0 = fast_exp2(fmaf(__uint_as_float(u[i]), scale2, -m_new));
+        float e1 = fast_exp2(fmaf(__uint_as_float(u[i + 1]), scale2, -m_new));
+        if (tail) {
+          if (c * 32 + i >= nvalid) e0 = 0.f;
+          if (c * 32 + i + 1 >= nvalid) e1 = 0.f;
+        }
+        lsum += e0 + e1;
+        if (p.drop_thresh) {
+          float s0, s1;
+          dropout_scale2(dseed, drow + (unsigned long long)(j * BKV + c * 32 + i), p.drop_thresh, p.drop_inv_keep, s0, s1);
+          e0 *= s0;
+          e1 *= s1;
+        }
+        pv[i] = e0;
+        pv[i + 1] = e1;
       }
-      store_tile_chunk(sP, tid, c * 32, pv);
+      store_tile_chunk(sP, rloc, c * 32, pv);
     }
-    l_run = l_run * corr + lsum;
+    l_part = l_part * corr + lsum;
     m_run = m_new;
 #pragma unroll
-    for (int i = 0; i < DH; ++i) o[i] *= corr;
+    for (int i = 0; i < 32; ++i) o[i] *= corr;
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
+      mbar_wait(&bars[2], ph);
       tc_fence_after();
       const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
 #pragma unroll
       for (int k = 0; k < BKV / 16; ++k)
         umma_bf16(tO, umma_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
                   umma_desc_sw128(va + k * 2048, 8192, 1024), idesc_o, k > 0);
-      umma_commit(&bars[3]);
+      umma_commit(&bars[4]);
     }
-    mbar_wait(&bars[3], ph);
+    mbar_wait(&bars[4], ph);
     __syncwarp();
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < DH / 32; ++c) {
+    if (tid == 0 && j + 1 < nkv) load_v(j + 1);  // PV(j) is complete: the V tile (and P) are free
+    {
       uint32_t u[32];
-      tmem_ld32(tO + lane_addr + c * 32, u);
+      tmem_ld32(tO + lane_addr + half * 32, u);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(u[i]);
+      for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(u[i]);
     }
-    tc_fence_before();
-    __syncthreads();  // everyone has drained S / O_blk and K/V/P before the next block overwrites them
+    tc_fence_before();  // the next S / PV products are issued only after a later __syncthreads
   }
+  xch[half * 128 + rloc] = l_part;
+  __syncthreads();
+  const float l_run = l_part + xch[(half ^ 1) * 128 + rloc];
   if (qrow < p.T) {
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    bf16* dst = p.ctx + ((long long)b * p.T + qrow) * p.d + h * DH;
+    bf16* dst = p.ctx + ((long long)b * p.T + qrow) * p.d + h * DH + half * 32;
 #pragma unroll
-    for (int i = 0; i < DH / 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       uint4 u;
       u.x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
       u.y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
@@ -200,7 +243,7 @@ __global__ void __launch_bounds__(ATT_THREADS) mqa_fwd_kernel(const __grid_const
       u.w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
       reinterpret_cast<uint4*>(dst)[i] = u;
     }
-    if (p.lse2) p.lse2[((long long)b * p.H + h) * p.T + qrow] = l_run > 0.f ? m_run + log2f(l_run) : -INFINITY;
+    if (p.lse2 && half == 0) p.lse2[((long long)b * p.H + h) * p.T + qrow] = l_run > 0.f ? m_run + log2f(l_run) : -INFINITY;
   }
   tc_fence_before();
   __syncthreads();
@@ -234,12 +277,6 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ dctx, const bf16* __r
 // while iteration it runs.
 // ------------------------------------------------------------------------------------------------
 constexpr int ATT_BWD_THREADS = 256;
-
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 __global__ void __launch_bounds__(ATT_BWD_THREADS) mqa_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                                   const __grid_constant__ CUtensorMap tm_do, const AttnParams p) {
@@ -512,7 +549,7 @@ extern "C" int tasr_mqa_attention_fwd(const void* qkv, int B, int T, int H, int 
   fill_params(&p, B, T, H, d, key_lengths, drop_p, seed);
   p.ctx = reinterpret_cast<bf16*>(ctx);
   p.lse2 = lse2;
-  constexpr int SMEM = 81920 + 64 + 1024;
+  constexpr int SMEM = 81920 + 64 + 1024 + 1024;  // tiles, barriers, row exchange, alignment slack
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(mqa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
