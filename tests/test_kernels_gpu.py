@@ -185,6 +185,48 @@ def test_mqa_attention_fwd_bwd(cuda, B, T, H, lens):
     assert rel_err(dqkv[:, d + 64:], gref[:, d + 64:]) < 2e-2
 
 
+def test_mqa_attention_dropout_mask_consistent(cuda):
+    """Dropout on the probabilities: the mask the forward applied is read back exactly (one-hot V), then forward and
+    backward are checked against float64 autograd with that same mask (model/attention.py:239 dropout_p)."""
+    B, T, H, p_drop, seed = 2, 128, 4, 0.25, 99
+    d = H * 64
+    lens = [128, 77]
+    g = torch.Generator().manual_seed(5)
+    qkv = bf(torch.randn(B * T, d + 128, generator=g) * 0.7)
+    kl = torch.tensor(lens, dtype=torch.int64)
+    kl_dev = kl.to(cuda)
+    pd = torch.zeros(B, H, T, T, dtype=torch.float64)
+    for blk in range(T // 64):
+        probe = qkv.clone().view(B, T, d + 128)
+        probe[:, :, d + 64:] = 0
+        for j in range(64):
+            probe[:, 64 * blk + j, d + 64 + j] = 1.0
+        c, _ = L.mqa_fwd(probe.view(B * T, d + 128).to(cuda), B, T, H, d, kl_dev, p_drop, seed)
+        pd[:, :, :, 64 * blk:64 * blk + 64] = c.double().cpu().view(B, T, H, 64).transpose(1, 2)
+    mask = (pd > 0).double()
+    frac = 1.0 - mask[0].mean().item()       # utterance 0 has every key valid
+    assert abs(frac - p_drop) < 0.02
+    x = qkv.double().requires_grad_(True)
+    q = x[:, :d].view(B, T, H, 64).transpose(1, 2)
+    k = x[:, d:d + 64].view(B, T, 1, 64).transpose(1, 2)
+    v = x[:, d + 64:].view(B, T, 1, 64).transpose(1, 2)
+    sc = (q @ k.transpose(-1, -2)) / 8.0
+    keymask = torch.arange(T)[None, :] >= kl[:, None]
+    sc = sc.masked_fill(keymask[:, None, None, :], float("-inf"))
+    pr = torch.softmax(sc, dim=-1) * mask / (1.0 - p_drop)
+    ref = (pr @ v).transpose(1, 2).reshape(B * T, d)
+    ctx, lse2 = L.mqa_fwd(qkv.to(cuda), B, T, H, d, kl_dev, p_drop, seed)
+    assert rel_err(ctx, ref.detach()) < 1.5e-2
+    dctx = bf(torch.randn(B * T, d, generator=g))
+    ref.backward(dctx.double())
+    dqkv = L.mqa_bwd(qkv.to(cuda), ctx, dctx.to(cuda), lse2, B, T, H, d, kl_dev, None, p_drop, seed)
+    torch.cuda.synchronize()
+    gref = x.grad
+    assert rel_err(dqkv[:, :d], gref[:, :d]) < 2.5e-2
+    assert rel_err(dqkv[:, d:d + 64], gref[:, d:d + 64]) < 2.5e-2
+    assert rel_err(dqkv[:, d + 64:], gref[:, d + 64:]) < 2.5e-2
+
+
 # ------------------------------------------------------------------ subsampler
 @pytest.mark.parametrize("B,T,d", [(2, 203, 256), (1, 64, 512), (3, 9, 256)])
 def test_conv1_im2col_and_bwd(cuda, B, T, d):

@@ -28,8 +28,14 @@ def timeit(name, fn, bytes_=0, iters=10):
         for _ in range(iters):
             fn()
         torch.cuda.synchronize()
-    us = sum(ev.device_time for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA
-             and "Memset" not in ev.name and "at::native" not in ev.name) / iters
+    evs = [ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and "at::native" not in ev.name]
+    us = sum(ev.device_time for ev in evs) / iters
+    parts = {}
+    for ev in evs:
+        k = ev.name.split("::")[-1].split("(")[0][:28]
+        parts[k] = parts.get(k, 0.0) + ev.device_time / iters
+    if len(parts) > 1:
+        name = name + " [" + ", ".join("%s %.1f" % kv for kv in parts.items()) + "]"
     print("%-28s %9.1f us   %7.2f TB/s (algorithmic %.1f MB)" % (name, us, bytes_ / us / 1e6 if bytes_ else 0, bytes_ / 1e6))
 
 

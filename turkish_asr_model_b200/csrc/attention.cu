@@ -52,9 +52,19 @@ __device__ __forceinline__ void store_tile_chunk(uint8_t* tile, int r, int c0, c
   }
 }
 
-// dropout index space: rows of even pitch so that (key, key + 1) pairs share one hash in forward and backward
-__device__ __forceinline__ unsigned long long drop_index(int b, int h, int H, int T, int q, int k) {
-  return (((unsigned long long)(b * H + h) * T + q) * (unsigned long long)((T + 1) & ~1)) + k;
+// dropout index space: element (b, h, q, key) -> ((b H + h) T + q) * even(T) + key, so (key, key + 1) pairs share a hash
+// Dropout mask of one (key, key + 1) pair inside a 32-key chunk: the chunk's hash base is computed once
+// (tasr_hash_pair_base of the chunk's first pair), pair j of the chunk costs one add + the mixer.  Forward and backward
+// walk the same 32-key chunks, so they see the same mask.  thresh_hi = thresh16 << 16.
+__device__ __forceinline__ void attn_drop_pair(uint32_t base32, uint32_t seed_hi, uint32_t j, uint32_t thresh_hi, bool& keep0,
+                                               bool& keep1) {
+  uint32_t x = base32 + j;
+  x ^= x >> 16; x *= 0x7FEB352Du;
+  x ^= seed_hi;
+  x ^= x >> 15; x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  keep0 = (x << 16) >= thresh_hi;  // low 16-bit lane >= thresh16
+  keep1 = x >= thresh_hi;          // high 16-bit lane >= thresh16
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -117,6 +127,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) mqa_fwd_kernel(const __grid_co
     load_v(0);
   }
   const unsigned long long dseed = (p.drop_thresh && p.seed_ptr) ? p.seed + *p.seed_ptr : p.seed;
+  const uint32_t dseed_hi = (uint32_t)(dseed >> 32), thresh_hi = p.drop_thresh << 16;
   const float scale2 = p.scale * LOG2E;
   float m_run = -INFINITY, l_part = 0.f;
   float o[32];
@@ -178,6 +189,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) mqa_fwd_kernel(const __grid_co
       tmem_ld32(tS + lane_addr + c * 32, u);
       tmem_ld_wait();
       float pv[32];
+      const uint32_t dbase = tasr_hash_pair_base(dseed, (drow + (unsigned long long)(j * BKV + c * 32)) >> 1);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         float e0 = fast_exp2(fmaf(__uint_as_float(u[i]), scale2, -m_new));
@@ -188,10 +200,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) mqa_fwd_kernel(const __grid_co
         }
         lsum += e0 + e1;
         if (p.drop_thresh) {
-          float s0, s1;
-          dropout_scale2(dseed, drow + (unsigned long long)(j * BKV + c * 32 + i), p.drop_thresh, p.drop_inv_keep, s0, s1);
-          e0 *= s0;
-          e1 *= s1;
+          bool k0, k1;
+          attn_drop_pair(dbase, dseed_hi, (uint32_t)(i >> 1), thresh_hi, k0, k1);
+          e0 = k0 ? e0 * p.drop_inv_keep : 0.f;
+          e1 = k1 ? e1 * p.drop_inv_keep : 0.f;
         }
         pv[i] = e0;
         pv[i + 1] = e1;
@@ -253,30 +265,65 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) mqa_fwd_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 // backward prep: delta[b,h,t] = sum_j dO[row, 64h+j] * O[row, 64h+j]   (one warp per (row, head))
 // ------------------------------------------------------------------------------------------------
-__global__ void attn_delta_kernel(const bf16* __restrict__ dctx, const bf16* __restrict__ ctx, int B, int T, int H, int d,
-                                  float* __restrict__ delta) {
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= (long long)B * T * H) return;
-  const long long row = warp / H;
-  const int h = (int)(warp - row * H);
-  const long long off = row * d + h * DH + lane * 2;
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(dctx + off));
-  const float2 c = __bfloat1622float2(*reinterpret_cast<const bf162*>(ctx + off));
-  const float s = warp_sum(a.x * c.x + a.y * c.y);
-  if (lane == 0) {
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ dctx, const bf16* __restrict__ ctx, int B, int T,
+                                                         int H, int d, float* __restrict__ delta) {
+  // 8 threads per (row, head), 8 elements (16 B) each
+  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long item = gidx >> 3;
+  const int sub = (int)(gidx & 7);
+  const bool ok = item < (long long)B * T * H;
+  float s = 0.f;
+  long long row = 0;
+  int h = 0;
+  if (ok) {
+    row = item / H;
+    h = (int)(item - row * H);
+    const long long off = row * d + h * DH + sub * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(dctx + off);
+    const uint4 c = *reinterpret_cast<const uint4*>(ctx + off);
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = unpack_bf16x2(av[i]), y = unpack_bf16x2(cv[i]);
+      s = fmaf(x.x, y.x, fmaf(x.y, y.y, s));
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && sub == 0) {
     const int b = (int)(row / T), t = (int)(row - (long long)b * T);
     delta[((long long)b * H + h) * T + t] = s;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: grid (ceil(T/128) kv blocks, B); loops over heads and query tiles.
-// 256 threads: warps 0-3 own columns [0,64) of the S / dP tiles, warps 4-7 columns [64,128) (one TMEM lane =
-// one query row per thread pair).  Q / dO tiles are double-buffered: the TMA for iteration it+1 is in flight
-// while iteration it runs.
+// backward: persistent, one CTA per SM.  Work unit = (utterance b, 128-key block, head, 128-query tile); the units of
+// the key blocks that exist (key-length aware) are dealt to the CTAs as equal contiguous ranges, so a CTA keeps K/V
+// and the dK/dV accumulators (TMEM) while it stays on one key block and adds them to the fp32 gradient buffer when it
+// leaves it.  512 threads: warp w owns TMEM lanes (= query rows) 32 (w % 4) .. + 31 and the 32-column chunk w / 4 of the
+// S / dP tiles (four threads per row).  Q / dO tiles are double-buffered, and the S / dP products of unit i+1 are issued right
+// behind the dV / dK / dQ products of unit i, so they run while unit i's dQ is drained.
 // ------------------------------------------------------------------------------------------------
-constexpr int ATT_BWD_THREADS = 256;
+constexpr int ATT_BWD_THREADS = 512;
+constexpr int ATT_BWD_MAX_B = 4096;
+
+struct BwdUnit {
+  int b, kblk, h, qi;
+  long long g;  // key-block index over the whole batch (b, kblk)
+};
+
+__device__ __forceinline__ BwdUnit decode_unit(long long u, int per, int nq, const int* __restrict__ pre, int& bhint) {
+  BwdUnit r;
+  r.g = u / per;
+  const int rem = (int)(u - r.g * per);
+  r.h = rem / nq;
+  r.qi = rem - r.h * nq;
+  while (pre[bhint + 1] <= r.g) ++bhint;
+  r.b = bhint;
+  r.kblk = (int)(r.g - pre[bhint]);
+  return r;
+}
 
 __global__ void __launch_bounds__(ATT_BWD_THREADS) mqa_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                                   const __grid_constant__ CUtensorMap tm_do, const AttnParams p) {
@@ -290,24 +337,13 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS) mqa_bwd_kernel(const __grid_c
   uint8_t* sDS = smem + 131072;   // 32 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 163840);  // kv, q0, q1, mma1, mma2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  int* pre = reinterpret_cast<int*>(smem + 163840 + 64);        // [B + 1] prefix of key blocks per utterance
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, half = warp >> 2;
+  const int quarter = warp & 3, cgrp = warp >> 2;
   const int rloc = quarter * 32 + lane;  // TMEM lane = row of the tile
-  const int j = blockIdx.x, b = blockIdx.y;
-  const int k0 = j * BKV;
-  const int Lk = p.key_len ? (int)max(0LL, min((long long)p.T, p.key_len[b])) : p.T;
   const int ld = p.d + 2 * DH;
-  const int krow = k0 + rloc;
 
-  if (k0 >= Lk) {  // fully masked key block: zero gradients
-    if (krow < p.T) {
-      uint4* dst = reinterpret_cast<uint4*>(p.dqkv + ((long long)b * p.T + krow) * ld + p.d) + half * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
-    }
-    return;
-  }
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
@@ -315,159 +351,207 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS) mqa_bwd_kernel(const __grid_c
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < p.B; i += ATT_BWD_THREADS) {
+    const int Lk = p.key_len ? (int)max(0LL, min((long long)p.T, p.key_len[i])) : p.T;
+    pre[i + 1] = (Lk + BKV - 1) / BKV;
+  }
   tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    pre[0] = 0;
+    for (int i = 1; i <= p.B; ++i) pre[i] += pre[i - 1];
+  }
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDK = tmem + 256, tDV = tmem + 320, tDQ = tmem + 384;
   const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
 
   const int nq = (p.T + BQ - 1) / BQ;
-  const int niter = p.H * nq;
-  auto issue_qdo = [&](int it) {  // thread 0 only
-    const int h = it / nq, q0 = (it - h * nq) * BQ, buf = it & 1;
-    uint64_t* bar = &bars[1 + buf];
-    mbar_expect_tx(bar, 32768);
-    tma_load_3d(sQ + buf * 16384, &tm_qkv, bar, h * DH, q0, b);
-    tma_load_3d(sQ + buf * 16384 + 8192, &tm_qkv, bar, h * DH, q0 + 64, b);
-    tma_load_3d(sDO + buf * 16384, &tm_do, bar, h * DH, q0, b);
-    tma_load_3d(sDO + buf * 16384 + 8192, &tm_do, bar, h * DH, q0 + 64, b);
-  };
-  if (tid == 0) {
-    mbar_expect_tx(&bars[0], 32768);
-    tma_load_3d(sK, &tm_qkv, &bars[0], p.d, k0, b);
-    tma_load_3d(sK + 8192, &tm_qkv, &bars[0], p.d, k0 + 64, b);
-    tma_load_3d(sV, &tm_qkv, &bars[0], p.d + DH, k0, b);
-    tma_load_3d(sV + 8192, &tm_qkv, &bars[0], p.d + DH, k0 + 64, b);
-    issue_qdo(0);
-  }
+  const int per = p.H * nq;
+  const long long U = (long long)pre[p.B] * per;
+  const long long u_begin = U * blockIdx.x / gridDim.x, u_end = U * (blockIdx.x + 1) / gridDim.x;
+  const int n = (int)(u_end - u_begin);
+
   const unsigned long long dseed = (p.drop_thresh && p.seed_ptr) ? p.seed + *p.seed_ptr : p.seed;
+  const uint32_t dseed_hi = (uint32_t)(dseed >> 32), thresh_hi = p.drop_thresh << 16;
   const float scale2 = p.scale * LOG2E;
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);     // Q K^T, dO V^T
   constexpr uint32_t idesc_t = umma_idesc_bf16(128, DH, 1, 1);      // P^T dO, dS^T Q
   constexpr uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);      // dS K
   const int Tp = (p.T + 1) & ~1;  // even row pitch of the dropout index space
 
-  for (int it = 0; it < niter; ++it) {
-    const int h = it / nq, qi = it - h * nq;
-    const int buf = it & 1;
-    const uint32_t ph = (uint32_t)it & 1u;          // mma barriers complete once per iteration
-    const uint32_t qph = (uint32_t)(it >> 1) & 1u;  // each q/dO buffer completes every other iteration
-    const int q0 = qi * BQ;
-    uint8_t* cQ = sQ + buf * 16384;
-    uint8_t* cDO = sDO + buf * 16384;
-    if (tid == 0) {
-      if (it + 1 < niter) issue_qdo(it + 1);  // the other buffer was released by the end of iteration it-1
-      if (it == 0) mbar_wait(&bars[0], 0);
-      mbar_wait(&bars[1 + buf], qph);
-      tc_fence_after();
-      const uint32_t qa = smem_u32(cQ), ka = smem_u32(sK), da = smem_u32(cDO), va = smem_u32(sV);
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k)
-        umma_bf16(tS, umma_desc_sw128(qa + k * 32, 16, 1024), umma_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k)
-        umma_bf16(tDP, umma_desc_sw128(da + k * 32, 16, 1024), umma_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
-      umma_commit(&bars[3]);
-    }
-    const int qrow = q0 + rloc;
-    const bool qvalid = qrow < p.T;
-    float lse2 = 0.f, delta = 0.f;
-    if (qvalid) {
-      lse2 = p.lse2[((long long)b * p.H + h) * p.T + qrow];
-      delta = p.delta[((long long)b * p.H + h) * p.T + qrow];
-    }
-    const bool row_ok = qvalid && lse2 != -INFINITY;
-    const unsigned long long drow = ((unsigned long long)(b * p.H + h) * p.T + qrow) * (unsigned long long)Tp;
-    mbar_wait(&bars[3], ph);
-    __syncwarp();
+  // ---- issuer-side helpers (thread 0 only) ----
+  uint32_t kv_phase = 0;
+  auto issue_qdo = [&](const BwdUnit& un, int buf) {
+    uint64_t* bar = &bars[1 + buf];
+    const int q0 = un.qi * BQ;
+    mbar_expect_tx(bar, 32768);
+    tma_load_3d(sQ + buf * 16384, &tm_qkv, bar, un.h * DH, q0, un.b);
+    tma_load_3d(sQ + buf * 16384 + 8192, &tm_qkv, bar, un.h * DH, q0 + 64, un.b);
+    tma_load_3d(sDO + buf * 16384, &tm_do, bar, un.h * DH, q0, un.b);
+    tma_load_3d(sDO + buf * 16384 + 8192, &tm_do, bar, un.h * DH, q0 + 64, un.b);
+  };
+  auto load_kv = [&](const BwdUnit& un) {
+    const int k0 = un.kblk * BKV;
+    mbar_expect_tx(&bars[0], 32768);
+    tma_load_3d(sK, &tm_qkv, &bars[0], p.d, k0, un.b);
+    tma_load_3d(sK + 8192, &tm_qkv, &bars[0], p.d, k0 + 64, un.b);
+    tma_load_3d(sV, &tm_qkv, &bars[0], p.d + DH, k0, un.b);
+    tma_load_3d(sV + 8192, &tm_qkv, &bars[0], p.d + DH, k0 + 64, un.b);
+    mbar_wait(&bars[0], kv_phase);
+    kv_phase ^= 1u;
+  };
+  auto issue_s_dp = [&](int i) {  // S = Q K^T and dP = dO V^T of local unit i
+    const int buf = i & 1;
+    mbar_wait(&bars[1 + buf], (uint32_t)(i >> 1) & 1u);
     tc_fence_after();
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int c = half * 2 + cc;  // 32-column chunk of the 128-key tile
-      uint32_t us[32], ud[32];
-      tmem_ld32(tS + lane_addr + c * 32, us);
-      tmem_ld32(tDP + lane_addr + c * 32, ud);
-      tmem_ld_wait();
-      float pv[32], dsv[32];
+    const uint32_t qa = smem_u32(sQ + buf * 16384), ka = smem_u32(sK), da = smem_u32(sDO + buf * 16384), va = smem_u32(sV);
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const int key = k0 + c * 32 + i;
-        float s0 = 1.f, s1 = 1.f;
-        if (p.drop_thresh) dropout_scale2(dseed, drow + key, p.drop_thresh, p.drop_inv_keep, s0, s1);
+    for (int k = 0; k < DH / 16; ++k)
+      umma_bf16(tS, umma_desc_sw128(qa + k * 32, 16, 1024), umma_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          float pr = 0.f, ds = 0.f;
-          if (row_ok && key + jj < Lk) {
-            const float ms = jj == 0 ? s0 : s1;
-            pr = fast_exp2(__uint_as_float(us[i + jj]) * scale2 - lse2);
-            ds = pr * (__uint_as_float(ud[i + jj]) * ms - delta) * p.scale;
-            pr *= ms;
-          }
-          pv[i + jj] = pr;
-          dsv[i + jj] = ds;
-        }
+    for (int k = 0; k < DH / 16; ++k)
+      umma_bf16(tDP, umma_desc_sw128(da + k * 32, 16, 1024), umma_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
+    umma_commit(&bars[3]);
+  };
+
+  if (n > 0) {
+    int bhint = 0;
+    BwdUnit cur = decode_unit(u_begin, per, nq, pre, bhint);
+    if (tid == 0) {
+      issue_qdo(cur, 0);
+      if (n > 1) {
+        int bh2 = bhint;
+        issue_qdo(decode_unit(u_begin + 1, per, nq, pre, bh2), 1);
       }
-      store_tile_chunk(sP, rloc, c * 32, pv);
-      store_tile_chunk(sDS, rloc, c * 32, dsv);
+      load_kv(cur);
+      issue_s_dp(0);
     }
-    tc_fence_before();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t pa = smem_u32(sP), sa = smem_u32(sDS), qa = smem_u32(cQ), da = smem_u32(cDO), ka = smem_u32(sK);
-#pragma unroll
-      for (int k = 0; k < BQ / 16; ++k)  // dV += P^T dO   (reduction over query rows)
-        umma_bf16(tDV, umma_desc_sw128(pa + k * 2048, 16384, 1024), umma_desc_sw128(da + k * 2048, 8192, 1024), idesc_t,
-                  (it > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < BQ / 16; ++k)  // dK += dS^T Q
-        umma_bf16(tDK, umma_desc_sw128(sa + k * 2048, 16384, 1024), umma_desc_sw128(qa + k * 2048, 8192, 1024), idesc_t,
-                  (it > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < BKV / 16; ++k)  // dQ = dS K    (reduction over keys)
-        umma_bf16(tDQ, umma_desc_sw128(sa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                  umma_desc_sw128(ka + k * 2048, 8192, 1024), idesc_q, k > 0);
-      umma_commit(&bars[4]);
-    }
-    mbar_wait(&bars[4], ph);
-    __syncwarp();
-    tc_fence_after();
-    {
-      uint32_t u[32];
-      tmem_ld32(tDQ + lane_addr + half * 32, u);
-      tmem_ld_wait();
+    bool first_in_group = true;
+    for (int i = 0; i < n; ++i) {
+      const int buf = i & 1;
+      const uint32_t ph = (uint32_t)i & 1u;
+      int bh1 = bhint;
+      BwdUnit nxt = cur;
+      const bool has_next = i + 1 < n;
+      if (has_next) nxt = decode_unit(u_begin + i + 1, per, nq, pre, bh1);
+      const bool next_same = has_next && nxt.g == cur.g;
+      const int b = cur.b, h = cur.h, k0 = cur.kblk * BKV, q0 = cur.qi * BQ;
+      const int Lk = p.key_len ? (int)max(0LL, min((long long)p.T, p.key_len[b])) : p.T;
+      uint8_t* cQ = sQ + buf * 16384;
+      uint8_t* cDO = sDO + buf * 16384;
+      const int qrow = q0 + rloc;
+      const bool qvalid = qrow < p.T;
+      float lse2 = 0.f, delta = 0.f;
       if (qvalid) {
-        float4* dst = reinterpret_cast<float4*>(p.dq_acc + ((long long)b * p.T + qrow) * p.d + h * DH + half * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          atomicAdd(dst + i, make_float4(__uint_as_float(u[4 * i]), __uint_as_float(u[4 * i + 1]),
-                                         __uint_as_float(u[4 * i + 2]), __uint_as_float(u[4 * i + 3])));
+        lse2 = p.lse2[((long long)b * p.H + h) * p.T + qrow];
+        delta = p.delta[((long long)b * p.H + h) * p.T + qrow];
       }
-    }
-    tc_fence_before();
-    __syncthreads();
-  }
-  // dK, dV of this key block (summed over heads and query tiles); half 0 writes dK, half 1 writes dV
-  {
-    bf16* dst = p.dqkv + ((long long)b * p.T + krow) * ld + p.d + half * DH;
+      // rows that do not exist (or saw no key): lse2 = +inf makes every probability exp2(-inf) = 0
+      if (!qvalid || lse2 == -INFINITY) lse2 = INFINITY;
+      const unsigned long long drow = ((unsigned long long)(b * p.H + h) * p.T + qrow) * (unsigned long long)Tp;
+      mbar_wait(&bars[3], ph);
+      __syncwarp();
+      tc_fence_after();
+      {
+        const int c = cgrp;  // 32-column chunk of the 128-key tile
+        uint32_t us[32], ud[32];
+        tmem_ld32(tS + lane_addr + c * 32, us);
+        tmem_ld32(tDP + lane_addr + c * 32, ud);
+        tmem_ld_wait();
+        float pv[32], dsv[32];
+        const uint32_t dbase = tasr_hash_pair_base(dseed, (drow + (unsigned long long)(k0 + c * 32)) >> 1);
+        const int nvalid = Lk - k0 - c * 32;  // keys of this chunk that exist
+        const float inv_keep = p.drop_thresh ? p.drop_inv_keep : 1.f;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t u[32];
-      tmem_ld32((half == 0 ? tDK : tDV) + c * 32 + lane_addr, u);
-      tmem_ld_wait();
-      if (krow < p.T) {
+        for (int i2 = 0; i2 < 32; i2 += 2) {
+          bool keep0 = true, keep1 = true;
+          if (p.drop_thresh) attn_drop_pair(dbase, dseed_hi, (uint32_t)(i2 >> 1), thresh_hi, keep0, keep1);
+          float pr0 = fast_exp2(fmaf(__uint_as_float(us[i2]), scale2, -lse2));
+          float pr1 = fast_exp2(fmaf(__uint_as_float(us[i2 + 1]), scale2, -lse2));
+          if (nvalid < 32) {  // only in the last key block of an utterance
+            if (i2 >= nvalid) pr0 = 0.f;
+            if (i2 + 1 >= nvalid) pr1 = 0.f;
+          }
+          const float m0 = keep0 ? inv_keep : 0.f, m1 = keep1 ? inv_keep : 0.f;
+          dsv[i2] = (pr0 * p.scale) * fmaf(__uint_as_float(ud[i2]), m0, -delta);
+          dsv[i2 + 1] = (pr1 * p.scale) * fmaf(__uint_as_float(ud[i2 + 1]), m1, -delta);
+          pv[i2] = pr0 * m0;
+          pv[i2 + 1] = pr1 * m1;
+        }
+        store_tile_chunk(sP, rloc, c * 32, pv);
+        store_tile_chunk(sDS, rloc, c * 32, dsv);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP), sa = smem_u32(sDS), qa = smem_u32(cQ), da = smem_u32(cDO), ka = smem_u32(sK);
+        const uint32_t acc0 = first_in_group ? 0u : 1u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(u[8 * i + 0]), __uint_as_float(u[8 * i + 1]));
-          v.y = pack_bf16x2(__uint_as_float(u[8 * i + 2]), __uint_as_float(u[8 * i + 3]));
-          v.z = pack_bf16x2(__uint_as_float(u[8 * i + 4]), __uint_as_float(u[8 * i + 5]));
-          v.w = pack_bf16x2(__uint_as_float(u[8 * i + 6]), __uint_as_float(u[8 * i + 7]));
-          reinterpret_cast<uint4*>(dst + c * 32)[i] = v;
+        for (int k = 0; k < BQ / 16; ++k)  // dV += P^T dO   (reduction over query rows)
+          umma_bf16(tDV, umma_desc_sw128(pa + k * 2048, 16384, 1024), umma_desc_sw128(da + k * 2048, 8192, 1024), idesc_t,
+                    k > 0 ? 1u : acc0);
+#pragma unroll
+        for (int k = 0; k < BQ / 16; ++k)  // dK += dS^T Q
+          umma_bf16(tDK, umma_desc_sw128(sa + k * 2048, 16384, 1024), umma_desc_sw128(qa + k * 2048, 8192, 1024), idesc_t,
+                    k > 0 ? 1u : acc0);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)  // dQ = dS K    (reduction over keys)
+          umma_bf16(tDQ, umma_desc_sw128(sa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    umma_desc_sw128(ka + k * 2048, 8192, 1024), idesc_q, k > 0);
+        umma_commit(&bars[4]);
+        if (next_same) issue_s_dp(i + 1);  // same K/V: S / dP of the next unit run while this unit's dQ is drained
+      }
+      mbar_wait(&bars[4], ph);
+      __syncwarp();
+      tc_fence_after();
+      if (tid == 0 && i + 2 < n) {  // this unit's Q / dO buffer is free again
+        int bh2 = bh1;
+        issue_qdo(decode_unit(u_begin + i + 2, per, nq, pre, bh2), buf);
+      }
+      {
+        uint32_t u[16];
+        tmem_ld16(tDQ + lane_addr + cgrp * 16, u);
+        tmem_ld_wait();
+        if (qvalid) {
+          float4* dst = reinterpret_cast<float4*>(p.dq_acc + ((long long)b * p.T + qrow) * ld + h * DH + cgrp * 16);
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2)
+            atomicAdd(dst + i2, make_float4(__uint_as_float(u[4 * i2]), __uint_as_float(u[4 * i2 + 1]),
+                                            __uint_as_float(u[4 * i2 + 2]), __uint_as_float(u[4 * i2 + 3])));
         }
       }
+      first_in_group = false;
+      if (!next_same) {
+        // leaving this key block: add dK (half 0) / dV (half 1), summed over the heads and query tiles seen, to the buffer
+        const int krow = k0 + rloc;
+        {
+          uint32_t u[32];
+          tmem_ld32(tDK + cgrp * 32 + lane_addr, u);  // tDK | tDV are adjacent: chunks 0,1 = dK, 2,3 = dV
+          tmem_ld_wait();
+          if (krow < Lk) {
+            float4* dst = reinterpret_cast<float4*>(p.dq_acc + ((long long)b * p.T + krow) * ld + p.d + cgrp * 32);
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2)
+              atomicAdd(dst + i2, make_float4(__uint_as_float(u[4 * i2]), __uint_as_float(u[4 * i2 + 1]),
+                                              __uint_as_float(u[4 * i2 + 2]), __uint_as_float(u[4 * i2 + 3])));
+          }
+        }
+        tc_fence_before();
+        __syncthreads();  // everyone has drained dK / dV before the next key block overwrites them (and K / V)
+        if (has_next && tid == 0) {
+          tc_fence_after();
+          load_kv(nxt);
+          issue_s_dp(i + 1);
+        }
+        first_in_group = true;
+      }
+      tc_fence_before();
+      cur = nxt;
+      bhint = bh1;
     }
   }
   tc_fence_before();
@@ -475,29 +559,33 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS) mqa_bwd_kernel(const __grid_c
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// dq (fp32 accumulate) -> inverse RoPE -> bf16 into dqkv[:, 0:d];  inverse RoPE in place on dk
-__global__ void __launch_bounds__(256) attn_dq_finalize_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv,
+// gradient buffer (M, d + 128) fp32 -> dqkv bf16: inverse RoPE on the q heads and on k, plain conversion of v.
+// A thread converts elements i..i+3 and i+32..i+35 of one head (i multiple of 4).
+__global__ void __launch_bounds__(256) attn_dq_finalize_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv,
                                                                long long M, int T, int d, const float* __restrict__ cs) {
   const int ld = d + 2 * DH;
-  const int pairs = (d + DH) >> 1;
-  const long long total = M * pairs;
+  const int quads = ld >> 3;  // (head, i4) with i4 < 8
+  const long long total = M * quads;
   for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
-    const long long row = idx / pairs;
-    const int pidx = (int)(idx - row * pairs);
-    const int head = pidx >> 5, i = pidx & 31;
-    const int t = (int)(row % T);
-    float c = 1.f, s = 0.f;
-    if (cs != nullptr) { c = cs[(t * 32 + i) * 2]; s = -cs[(t * 32 + i) * 2 + 1]; }
-    bf16* o = dqkv + row * ld + head * DH;
-    float x1, x2;
-    if (head * DH < d) {
-      const float* src = dq_acc + row * d + head * DH;
-      x1 = src[i]; x2 = src[i + 32];
-    } else {
-      x1 = __bfloat162float(o[i]); x2 = __bfloat162float(o[i + 32]);
+    const long long row = idx / quads;
+    const int qidx = (int)(idx - row * quads);
+    const int head = qidx >> 3, i = (qidx & 7) << 2;
+    const float* src = acc + row * ld + head * DH;
+    const float4 x1 = *reinterpret_cast<const float4*>(src + i), x2 = *reinterpret_cast<const float4*>(src + i + 32);
+    float4 c0 = make_float4(1.f, 0.f, 1.f, 0.f), c1 = c0;  // (cos, sin) pairs
+    if (cs != nullptr && head * DH < d + DH) {  // rotated heads: q heads and k
+      const int t = (int)(row % T);
+      c0 = *reinterpret_cast<const float4*>(cs + (t * 32 + i) * 2);
+      c1 = *reinterpret_cast<const float4*>(cs + (t * 32 + i) * 2 + 4);
     }
-    o[i] = __float2bfloat16(x1 * c - x2 * s);
-    o[i + 32] = __float2bfloat16(x2 * c + x1 * s);
+    bf16* o = dqkv + row * ld + head * DH;
+    uint2 lo, hi;
+    lo.x = pack_bf16x2(x1.x * c0.x + x2.x * c0.y, x1.y * c0.z + x2.y * c0.w);
+    lo.y = pack_bf16x2(x1.z * c1.x + x2.z * c1.y, x1.w * c1.z + x2.w * c1.w);
+    hi.x = pack_bf16x2(x2.x * c0.x - x1.x * c0.y, x2.y * c0.z - x1.y * c0.w);
+    hi.y = pack_bf16x2(x2.z * c1.x - x1.z * c1.y, x2.w * c1.z - x1.w * c1.w);
+    *reinterpret_cast<uint2*>(o + i) = lo;
+    *reinterpret_cast<uint2*>(o + i + 32) = hi;
   }
 }
 
@@ -563,7 +651,7 @@ extern "C" int tasr_mqa_attention_fwd(const void* qkv, int B, int T, int H, int 
 }
 
 extern "C" size_t tasr_mqa_attention_bwd_workspace_bytes(int B, int T, int H, int d) {
-  return (size_t)B * H * T * sizeof(float) + (size_t)B * T * d * sizeof(float) + 256;
+  return (size_t)B * H * T * sizeof(float) + (size_t)B * T * (d + 2 * DH) * sizeof(float) + 256;
 }
 
 // dqkv (B*T, d+128) bf16 out: gradients w.r.t. the PRE-RoPE q | k | v when cos_sin != NULL (the inverse
@@ -572,13 +660,13 @@ extern "C" int tasr_mqa_attention_bwd(const void* qkv, const void* ctx, const vo
                                       int H, int d, const int64_t* key_lengths, float drop_p, uint64_t seed,
                                       const float* cos_sin, void* dqkv, void* workspace, size_t workspace_bytes,
                                       tasr_stream_t stream) {
-  if (B <= 0 || T <= 0 || H <= 0 || d != H * DH) return TASR_ERR_SHAPE;
+  if (B <= 0 || B > ATT_BWD_MAX_B || T <= 0 || H <= 0 || d != H * DH) return TASR_ERR_SHAPE;
   if (workspace_bytes < tasr_mqa_attention_bwd_workspace_bytes(B, T, H, d)) return TASR_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* delta = reinterpret_cast<float*>(workspace);
   size_t off = ((size_t)B * H * T * sizeof(float) + 255) & ~(size_t)255;
   float* dq_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + off);
-  cudaError_t e = cudaMemsetAsync(dq_acc, 0, (size_t)B * T * d * sizeof(float), st);
+  cudaError_t e = cudaMemsetAsync(dq_acc, 0, (size_t)B * T * (d + 2 * DH) * sizeof(float), st);
   if (e != cudaSuccess) return tasr_set_cuda_error(e);
   CUtensorMap tm_qkv, tm_do;
   int rc = make_tmap_3d(&tm_qkv, qkv, d + 2 * DH, T, B, d + 2 * DH);
@@ -586,7 +674,7 @@ extern "C" int tasr_mqa_attention_bwd(const void* qkv, const void* ctx, const vo
   rc = make_tmap_3d(&tm_do, dctx, d, T, B, d);
   if (rc) return rc;
   const long long nw = (long long)B * T * H;
-  attn_delta_kernel<<<cdiv(nw * 32, 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(dctx), reinterpret_cast<const bf16*>(ctx),
+  attn_delta_kernel<<<cdiv(nw * 8, 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(dctx), reinterpret_cast<const bf16*>(ctx),
                                                         B, T, H, d, delta);
   TASR_CHECK_LAUNCH();
   AttnParams p;
@@ -595,17 +683,24 @@ extern "C" int tasr_mqa_attention_bwd(const void* qkv, const void* ctx, const vo
   p.delta = delta;
   p.dq_acc = dq_acc;
   p.dqkv = reinterpret_cast<bf16*>(dqkv);
-  constexpr int SMEM = 163840 + 64 + 1024;
+  constexpr int SMEM_MAX = 163840 + 64 + (ATT_BWD_MAX_B + 1) * 4 + 1024;
+  const int smem_bytes = 163840 + 64 + (B + 1) * 4 + 1024;
   static bool attr_done = false;
+  static int n_sms = 148;
   if (!attr_done) {
-    e = cudaFuncSetAttribute(mqa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    e = cudaFuncSetAttribute(mqa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e != cudaSuccess) return tasr_set_cuda_error(e);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sms <= 0) n_sms = 148;
     attr_done = true;
   }
-  dim3 grid(cdiv(T, BKV), B);
-  mqa_bwd_kernel<<<grid, ATT_BWD_THREADS, SMEM, st>>>(tm_qkv, tm_do, p);
+  const long long max_units = (long long)B * cdiv(T, BKV) * H * cdiv(T, BQ);
+  const int grid = (int)imin64(n_sms, max_units);
+  mqa_bwd_kernel<<<grid, ATT_BWD_THREADS, smem_bytes, st>>>(tm_qkv, tm_do, p);
   TASR_CHECK_LAUNCH();
-  const long long total = (long long)B * T * ((d + DH) / 2);
+  const long long total = (long long)B * T * ((d + 2 * DH) / 8);
   attn_dq_finalize_kernel<<<(int)imin64((long long)148 * 8, (total + 255) / 256), 256, 0, st>>>(
       dq_acc, reinterpret_cast<bf16*>(dqkv), (long long)B * T, T, d, cos_sin);
   TASR_CHECK_LAUNCH();
