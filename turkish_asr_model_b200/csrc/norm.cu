@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(NT) bn_silu_bwd_apply_kernel(const bf16* __res
 // per-group sums, the partial sums are exchanged through distributed shared memory, and the rows are normalised
 // straight from shared memory: x is read from global memory exactly once (the two-kernel path reads it twice).
 constexpr int GN_CL = 8;
+constexpr long long GN_FUSED_MAX_SLICE = 8ll << 20;  // bytes of one utterance (T x d fp32) kept hot in L2 between the passes
 
 template <bool OUT_BF16>
 __global__ void __cluster_dims__(GN_CL, 1, 1) __launch_bounds__(NT)
@@ -374,7 +375,6 @@ gn_fused_fwd_kernel(const float* __restrict__ x, int T, int d, int G, int rows_p
                     const float* __restrict__ gamma, const float* __restrict__ beta, void* __restrict__ out,
                     float* __restrict__ stats_out) {
   cg::cluster_group cluster = cg::this_cluster();
-  extern __shared__ __align__(16) float sh_rows[];       // rows_per_cta * d
   __shared__ float part[64][2];                          // this CTA's per-group (sum, sumsq)
   __shared__ float sh_s[NT], sh_ss[NT];
   __shared__ float sh_mean[64], sh_rstd[64];
@@ -386,7 +386,6 @@ gn_fused_fwd_kernel(const float* __restrict__ x, int T, int d, int G, int rows_p
 #pragma unroll 4
   for (int t = t0 + rl; t < t1; t += rlanes) {
     const float4 v = ld4(x + ((long long)b * T + t) * d + col);
-    *reinterpret_cast<float4*>(sh_rows + (long long)(t - t0) * d + col) = v;
     s += (v.x + v.y) + (v.z + v.w);
     ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
   }
@@ -431,12 +430,12 @@ gn_fused_fwd_kernel(const float* __restrict__ x, int T, int d, int G, int rows_p
   const float4 ga = ld4(gamma + col), be = ld4(beta + col);
 #pragma unroll 4
   for (int t = t0 + rl; t < t1; t += rlanes) {
-    float4 v = *reinterpret_cast<const float4*>(sh_rows + (long long)(t - t0) * d + col);
+    const long long off = ((long long)b * T + t) * d + col;
+    float4 v = ld4(x + off);  // second read of this CTA's slice: served by L2
     v.x = (v.x - mean) * rstd * ga.x + be.x;
     v.y = (v.y - mean) * rstd * ga.y + be.y;
     v.z = (v.z - mean) * rstd * ga.z + be.z;
     v.w = (v.w - mean) * rstd * ga.w + be.w;
-    const long long off = ((long long)b * T + t) * d + col;
     if (OUT_BF16) st4_bf16(reinterpret_cast<bf16*>(out) + off, v);
     else *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + off) = v;
   }
@@ -452,11 +451,9 @@ gn_fused_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, in
                     const unsigned long long* __restrict__ seed_ptr) {
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) float sh_dyn2[];
-  // layout: xhat rows (rows*d f32) | dy rows (rows*d f32) | part a (d) | part c (d) | tot a (d) | tot c (d) | S1 (G) | S2 (G)
+  // layout: part a (d) | part c (d) | tot a (d) | tot c (d) | S1 (G) | S2 (G)
   const int b = blockIdx.x / GN_CL, rank = blockIdx.x % GN_CL;
-  float* sx = sh_dyn2;
-  float* sdy = sx + (long long)rows_per_cta * d;
-  float* pa = sdy + (long long)rows_per_cta * d;
+  float* pa = sh_dyn2;
   float* pc = pa + d;
   float* ta = pc + d;
   float* tcx = ta + d;
@@ -471,14 +468,12 @@ gn_fused_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, in
   const float mean = stats[((long long)b * G + g) * 2], rstd = stats[((long long)b * G + g) * 2 + 1];
   const int t0 = rank * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
   float4 a = make_float4(0, 0, 0, 0), c = make_float4(0, 0, 0, 0);
-#pragma unroll 2
+#pragma unroll 4
   for (int t = t0 + rl; t < t1; t += rlanes) {
     const long long off = ((long long)b * T + t) * d + col;
     float4 xv = ld4(x + off);
     const float4 g4 = DY_BF16 ? ld4_bf16(reinterpret_cast<const bf16*>(dy) + off) : ld4(reinterpret_cast<const float*>(dy) + off);
     xv.x = (xv.x - mean) * rstd; xv.y = (xv.y - mean) * rstd; xv.z = (xv.z - mean) * rstd; xv.w = (xv.w - mean) * rstd;
-    *reinterpret_cast<float4*>(sx + (long long)(t - t0) * d + col) = xv;
-    *reinterpret_cast<float4*>(sdy + (long long)(t - t0) * d + col) = g4;
     a.x += g4.x * xv.x; a.y += g4.y * xv.y; a.z += g4.z * xv.z; a.w += g4.w * xv.w;
     c.x += g4.x; c.y += g4.y; c.z += g4.z; c.w += g4.w;
   }
@@ -523,11 +518,12 @@ gn_fused_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, in
   cluster.sync();  // peers have finished reading this CTA's partial sums; S1/S2 visible to the whole CTA
   const float s1 = s1s[g], s2 = s2s[g];
   const float4 ga = ld4(gamma + col);
-#pragma unroll 2
+#pragma unroll 4
   for (int t = t0 + rl; t < t1; t += rlanes) {
     const long long off = ((long long)b * T + t) * d + col;
-    const float4 xh = *reinterpret_cast<const float4*>(sx + (long long)(t - t0) * d + col);
-    const float4 g4 = *reinterpret_cast<const float4*>(sdy + (long long)(t - t0) * d + col);
+    float4 xh = ld4(x + off);  // second read of this CTA's slice of x and dy: served by L2
+    const float4 g4 = DY_BF16 ? ld4_bf16(reinterpret_cast<const bf16*>(dy) + off) : ld4(reinterpret_cast<const float*>(dy) + off);
+    xh.x = (xh.x - mean) * rstd; xh.y = (xh.y - mean) * rstd; xh.z = (xh.z - mean) * rstd; xh.w = (xh.w - mean) * rstd;
     float4 r;
     r.x = rstd * (g4.x * ga.x - s1 - xh.x * s2);
     r.y = rstd * (g4.y * ga.y - s1 - xh.y * s2);
@@ -578,22 +574,12 @@ extern "C" int tasr_groupnorm_fwd(const float* x, int B, int T, int d, int G, fl
   if (!gn_shape_ok(d, G) || B <= 0 || T <= 0) return TASR_ERR_SHAPE;
   if (workspace_bytes < tasr_groupnorm_workspace_bytes(B, T, d)) return TASR_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  {  // single-pass cluster kernel when one eighth of an utterance fits in shared memory
+  if ((long long)T * d * sizeof(float) <= GN_FUSED_MAX_SLICE) {  // one cluster per utterance; its slice is re-read through L2
     const int frows = cdiv(T, GN_CL);
-    const size_t fsm = (size_t)frows * d * sizeof(float);
-    if (fsm <= 200 * 1024) {
-      static bool attr_done = false;
-      if (!attr_done) {
-        cudaError_t e1 = cudaFuncSetAttribute(gn_fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaError_t e2 = cudaFuncSetAttribute(gn_fused_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) return tasr_set_cuda_error(e1 != cudaSuccess ? e1 : e2);
-        attr_done = true;
-      }
-      if (out_bf16) gn_fused_fwd_kernel<true><<<B * GN_CL, NT, fsm, st>>>(x, T, d, G, frows, eps, gamma, beta, out, stats);
-      else gn_fused_fwd_kernel<false><<<B * GN_CL, NT, fsm, st>>>(x, T, d, G, frows, eps, gamma, beta, out, stats);
-      TASR_CHECK_LAUNCH();
-      return TASR_OK;
-    }
+    if (out_bf16) gn_fused_fwd_kernel<true><<<B * GN_CL, NT, 0, st>>>(x, T, d, G, frows, eps, gamma, beta, out, stats);
+    else gn_fused_fwd_kernel<false><<<B * GN_CL, NT, 0, st>>>(x, T, d, G, frows, eps, gamma, beta, out, stats);
+    TASR_CHECK_LAUNCH();
+    return TASR_OK;
   }
   const int rows = gn_rows_per_cta(B, T), nchunk = cdiv(T, rows);
   float* partial = reinterpret_cast<float*>(workspace);
@@ -616,26 +602,17 @@ extern "C" int tasr_groupnorm_bwd(const void* dy, int dy_bf16, const float* x, i
   if (!gn_shape_ok(d, G) || B <= 0 || T <= 0) return TASR_ERR_SHAPE;
   if (workspace_bytes < tasr_groupnorm_workspace_bytes(B, T, d)) return TASR_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  {
+  if ((long long)T * d * sizeof(float) <= GN_FUSED_MAX_SLICE) {
     const int frows = cdiv(T, GN_CL);
-    const size_t fsm = ((size_t)2 * frows * d + 4 * d + 2 * G) * sizeof(float);
-    if (fsm <= 190 * 1024) {
-      static bool attr_done = false;
-      if (!attr_done) {
-        cudaError_t e1 = cudaFuncSetAttribute(gn_fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);
-        cudaError_t e2 = cudaFuncSetAttribute(gn_fused_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) return tasr_set_cuda_error(e1 != cudaSuccess ? e1 : e2);
-        attr_done = true;
-      }
-      if (dy_bf16)
-        gn_fused_bwd_kernel<true><<<B * GN_CL, NT, fsm, st>>>(dy, x, T, d, G, frows, stats, gamma, dres, accumulate, dgamma, dbeta,
-                                                             cout_, cast_alpha, cthresh, cinv, cast_seed, g_tasr_seed_ptr);
-      else
-        gn_fused_bwd_kernel<false><<<B * GN_CL, NT, fsm, st>>>(dy, x, T, d, G, frows, stats, gamma, dres, accumulate, dgamma, dbeta,
-                                                              cout_, cast_alpha, cthresh, cinv, cast_seed, g_tasr_seed_ptr);
-      TASR_CHECK_LAUNCH();
-      return TASR_OK;
-    }
+    const size_t fsm = ((size_t)4 * d + 2 * G) * sizeof(float);
+    if (dy_bf16)
+      gn_fused_bwd_kernel<true><<<B * GN_CL, NT, fsm, st>>>(dy, x, T, d, G, frows, stats, gamma, dres, accumulate, dgamma, dbeta,
+                                                           cout_, cast_alpha, cthresh, cinv, cast_seed, g_tasr_seed_ptr);
+    else
+      gn_fused_bwd_kernel<false><<<B * GN_CL, NT, fsm, st>>>(dy, x, T, d, G, frows, stats, gamma, dres, accumulate, dgamma, dbeta,
+                                                            cout_, cast_alpha, cthresh, cinv, cast_seed, g_tasr_seed_ptr);
+    TASR_CHECK_LAUNCH();
+    return TASR_OK;
   }
   const int rows = gn_rows_per_cta(B, T), nchunk = cdiv(T, rows);
   float* partial = reinterpret_cast<float*>(workspace);
