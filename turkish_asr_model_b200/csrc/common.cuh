@@ -71,6 +71,21 @@ __device__ __forceinline__ float silu_gradf_(float x) {
   float s = sigmoidf_(x);
   return s * (1.f + x * (1.f - s));
 }
+// MUFU.TANH forms: sigmoid(x) = 1/2 + tanh(x/2)/2 (one SFU op instead of ex2 + rcp)
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+// d/dx silu(x) = (1 + t)(1 + h (1 - t)) / 2,  h = x/2, t = tanh(h)
+__device__ __forceinline__ float silu_grad_tanh(float x) {
+  const float h = 0.5f * x, t = tanh_approx(h);
+  return 0.5f * (1.f + t) * fmaf(h, 1.f - t, 1.f);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   bf162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -296,12 +296,6 @@ constexpr int PX = 5;               // output columns per item (F1 = 40 -> 8 ite
 constexpr int PCOLS = 2 * PX + 1;   // 11 patch columns; 3 x 11 = 33 patch values: lane l stages value l, lane 0 also value 32
 constexpr int PSLOT = 3 * (PCOLS + 1);
 
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 // A warp keeps one (column group, channel slice) for the whole kernel and walks output rows with a fixed stride, so the
 // per-item index arithmetic is a handful of adds (no divisions), and the backward's accumulators stay on one slice.
 struct WarpWalk {

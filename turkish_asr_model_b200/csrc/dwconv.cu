@@ -1,32 +1,64 @@
 // Depthwise Conv1d (kernel 31, zero pad 15) along time on token-major (B, T, d) bf16 tensors, with the
 // BatchNorm partial statistics fused into the forward, and (backward) the weight / bias gradient and the
-// GLU backward fused into one kernel.  Halo tile staged in shared memory, sliding register window.
+// GLU backward fused into one kernel.  Halo tile staged in shared memory, sliding register window, packed fp32x2 FMAs.
 // Replaces (reference): model/conformer.py:63-67,83 depthwise_conv (cuDNN depthwise + 2 transposes),
 //   the GLU backward of :82, and the statistics pass of BatchNorm1d :84.
 #include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int KW = 31, HALO = 15;
-constexpr int TT = 64;        // time steps per CTA
-constexpr int CC = 64;        // channels per CTA (32 bf16x2 lanes)
-constexpr int OPT = 8;        // outputs per thread
+constexpr int TT = 128;       // time steps per tile
+constexpr int CC = 64;        // channels per CTA (32 channel-pair lanes)
+constexpr int OPT = 16;       // outputs per thread
 constexpr int DW_THREADS = 256;  // 32 channel-pair lanes x 8 strips
 constexpr int ROWS = TT + 2 * HALO;
 
+// All global loads of a staging pass are issued before the first shared-memory store (fixed trip counts, values held in
+// registers): a load -> store loop with a run-time bound is compiled into one exposed DRAM round trip per iteration.
 __device__ __forceinline__ void load_tile(bf162 (*tile)[CC / 2], const bf16* __restrict__ src, int b, int T, int d, int t0,
                                           int c0) {
   // ROWS x 128 B, 8 threads (16 B each) per row
-  for (int i = threadIdx.x; i < ROWS * 8; i += DW_THREADS) {
+  constexpr int N = ROWS * 8, IT = (N + DW_THREADS - 1) / DW_THREADS;
+  uint4 val[IT];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = threadIdx.x + it * DW_THREADS;
     const int r = i >> 3, v = i & 7;
     const int t = t0 - HALO + r;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (t >= 0 && t < T) val = *reinterpret_cast<const uint4*>(src + ((long long)b * T + t) * d + c0 + v * 8);
-    *reinterpret_cast<uint4*>(&tile[r][v * 4]) = val;
+    val[it] = make_uint4(0, 0, 0, 0);
+    if (i < N && t >= 0 && t < T) val[it] = *reinterpret_cast<const uint4*>(src + ((long long)b * T + t) * d + c0 + v * 8);
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = threadIdx.x + it * DW_THREADS;
+    if (i < N) *reinterpret_cast<uint4*>(&tile[i >> 3][(i & 7) * 4]) = val[it];
+  }
+}
+
+// The (d, 31) weight rows of this CTA's 64 channels are one contiguous run: read it coalesced and keep it as
+// [tap][channel pair] so that a thread's 31 taps are conflict-free 8-byte reads.
+__device__ __forceinline__ void load_weights(float2 (*wsm)[CC / 2], const float* __restrict__ weight, int c0) {
+  float* flat = reinterpret_cast<float*>(wsm);
+  constexpr int N = CC * KW, IT = (N + DW_THREADS - 1) / DW_THREADS;
+  float val[IT];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = threadIdx.x + it * DW_THREADS;
+    val[it] = i < N ? weight[(long long)c0 * KW + i] : 0.f;
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = threadIdx.x + it * DW_THREADS;
+    const int c = i / KW, k = i - c * KW;
+    if (i < N) flat[(k * (CC / 2) + (c >> 1)) * 2 + (c & 1)] = val[it];
   }
 }
 
 // out[t] = bias + sum_k in[t + k - 15] * w[k]      (FLIP: w index 30 - k, used for the input gradient)
+// packed fp32x2 FMAs on the channel pair
 template <bool FLIP>
 __device__ __forceinline__ void conv_strip(const bf162 (*tile)[CC / 2], int lane, int strip, const float2* wreg, float2* acc) {
 #pragma unroll
@@ -35,31 +67,29 @@ __device__ __forceinline__ void conv_strip(const bf162 (*tile)[CC / 2], int lane
 #pragma unroll
     for (int o = 0; o < OPT; ++o) {
       const int k = j - o;
-      if (k >= 0 && k < KW) {
-        const float2 w = wreg[FLIP ? (KW - 1 - k) : k];
-        acc[o].x = fmaf(v.x, w.x, acc[o].x);
-        acc[o].y = fmaf(v.y, w.y, acc[o].y);
-      }
+      if (k >= 0 && k < KW) acc[o] = __ffma2_rn(v, wreg[FLIP ? (KW - 1 - k) : k], acc[o]);
     }
   }
 }
 
 // weight (d, 31) fp32 [reference layout (d,1,31)], bias (d)
-__global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const bf16* __restrict__ u, int T, int d,
-                                                                const float* __restrict__ weight,
-                                                                const float* __restrict__ bias, bf16* __restrict__ out,
-                                                                float* __restrict__ bn_partial) {
+__global__ void __launch_bounds__(DW_THREADS, 2) dwconv_fwd_kernel(const bf16* __restrict__ u, int T, int d,
+                                                                   const float* __restrict__ weight,
+                                                                   const float* __restrict__ bias, bf16* __restrict__ out,
+                                                                   float* __restrict__ bn_partial) {
   __shared__ __align__(16) bf162 tile[ROWS][CC / 2];
+  __shared__ __align__(16) float2 wsm[KW][CC / 2];
   __shared__ float red[8][CC][2];
   const int c0 = blockIdx.x * CC, t0 = blockIdx.y * TT, b = blockIdx.z;
   const int lane = threadIdx.x & 31, strip = threadIdx.x >> 5;
+  load_weights(wsm, weight, c0);
   load_tile(tile, u, b, T, d, t0, c0);
-  float2 wreg[KW];
   const int ch = c0 + 2 * lane;
-#pragma unroll
-  for (int k = 0; k < KW; ++k) wreg[k] = make_float2(weight[ch * KW + k], weight[(ch + 1) * KW + k]);
   const float2 bv = make_float2(bias[ch], bias[ch + 1]);
   __syncthreads();
+  float2 wreg[KW];
+#pragma unroll
+  for (int k = 0; k < KW; ++k) wreg[k] = wsm[k][lane];
   float2 acc[OPT];
 #pragma unroll
   for (int o = 0; o < OPT; ++o) acc[o] = bv;
@@ -92,18 +122,20 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const bf16* __re
 }
 
 // Backward, kernel A: du = corr(dw, flipped weight) with the GLU backward fused -> dab (M, 2d) (or du).
-__global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_data_kernel(const bf16* __restrict__ dwv, const bf16* __restrict__ ab,
-                                                                     int T, int d, const float* __restrict__ weight,
-                                                                     bf16* __restrict__ dab, bf16* __restrict__ du_out) {
+__global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_data_kernel(const bf16* __restrict__ dwv, const bf16* __restrict__ ab,
+                                                                        int T, int d, const float* __restrict__ weight,
+                                                                        bf16* __restrict__ dab, bf16* __restrict__ du_out) {
   __shared__ __align__(16) bf162 tile[ROWS][CC / 2];
+  __shared__ __align__(16) float2 wsm[KW][CC / 2];
   const int c0 = blockIdx.x * CC, t0 = blockIdx.y * TT, b = blockIdx.z;
   const int lane = threadIdx.x & 31, strip = threadIdx.x >> 5;
   const int ch = c0 + 2 * lane;
+  load_weights(wsm, weight, c0);
   load_tile(tile, dwv, b, T, d, t0, c0);
+  __syncthreads();
   float2 wreg[KW];
 #pragma unroll
-  for (int k = 0; k < KW; ++k) wreg[k] = make_float2(weight[ch * KW + k], weight[(ch + 1) * KW + k]);
-  __syncthreads();
+  for (int k = 0; k < KW; ++k) wreg[k] = wsm[k][lane];
   float2 acc[OPT];
 #pragma unroll
   for (int o = 0; o < OPT; ++o) acc[o] = make_float2(0.f, 0.f);
@@ -116,7 +148,7 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_data_kernel(const bf16*
       if (ab != nullptr) {
         const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + ch));
         const float2 gt = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + d + ch));
-        const float s0 = sigmoidf_(gt.x), s1 = sigmoidf_(gt.y);
+        const float s0 = fmaf(0.5f, tanh_approx(0.5f * gt.x), 0.5f), s1 = fmaf(0.5f, tanh_approx(0.5f * gt.y), 0.5f);
         *reinterpret_cast<bf162*>(dab + row * 2 * d + ch) = __floats2bfloat162_rn(acc[o].x * s0, acc[o].y * s1);
         *reinterpret_cast<bf162*>(dab + row * 2 * d + d + ch) =
             __floats2bfloat162_rn(acc[o].x * a.x * s0 * (1.f - s0), acc[o].y * a.y * s1 * (1.f - s1));
@@ -128,65 +160,118 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_data_kernel(const bf16*
 }
 
 // Backward, kernel B: dweight[c][k] += sum_t dw[t,c] * u[t+k-15,c], dbias[c] += sum_t dw[t,c].
-// lane = channel pair, warp w = taps 4w..4w+3 (sliding 4-value window over u); a CTA walks a segment of time tiles
-// with the accumulators in registers and issues its atomics once.
+// lane = channel pair; warp w: tap group w & 3 (taps 8g..8g+7, a sliding 8-value window over u) and time half w >> 2 of
+// each tile.  The tiles are converted to fp32 pairs once when they are staged, so the inner loop is 2 LDS.64 + 8 FFMA2
+// per time step.  A CTA walks a segment of time tiles with the accumulators in registers and issues its atomics once.
+constexpr int WG_TAPS = 8;
 __global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_weight_kernel(const bf16* __restrict__ dwv, const bf16* __restrict__ u,
                                                                        int T, int d, float* __restrict__ dweight,
                                                                        float* __restrict__ dbias, int tiles_per_cta) {
-  __shared__ __align__(16) bf162 utile[ROWS][CC / 2];
-  __shared__ __align__(16) bf162 gtile[TT][CC / 2];
+  extern __shared__ __align__(16) float2 dsm[];
+  float2 (*utile)[CC / 2] = reinterpret_cast<float2 (*)[CC / 2]>(dsm);                       // [ROWS + 1]
+  float2 (*gtile)[CC / 2] = reinterpret_cast<float2 (*)[CC / 2]>(dsm + (ROWS + 1) * (CC / 2));  // [TT]
   const int c0 = blockIdx.x * CC, b = blockIdx.z;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ch = c0 + 2 * lane;
-  const int tap0 = 4 * w;
-  float2 acc[4];
+  const int tg = w & 3, th = w >> 2;
+  const int tap0 = WG_TAPS * tg;
+  float2 acc[WG_TAPS];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
+  for (int k = 0; k < WG_TAPS; ++k) acc[k] = make_float2(0.f, 0.f);
   float2 gsum = make_float2(0.f, 0.f);
   const int ntiles = (T + TT - 1) / TT;
   const int tile_begin = blockIdx.y * tiles_per_cta, tile_end = min(ntiles, tile_begin + tiles_per_cta);
   for (int ti = tile_begin; ti < tile_end; ++ti) {
     const int t0 = ti * TT;
     __syncthreads();
-    load_tile(utile, u, b, T, d, t0, c0);
-    for (int i = threadIdx.x; i < TT * 8; i += DW_THREADS) {
+    // stage u rows t0-15 .. t0+TT+15 (+1 zero row: tap 31 does not exist) and dw rows t0 .. t0+TT-1 as fp32 pairs;
+    // all loads first, then the conversions and stores
+    constexpr int NU = (ROWS + 1) * 8, ITU = (NU + DW_THREADS - 1) / DW_THREADS, ITG = TT * 8 / DW_THREADS;
+    uint4 uv[ITU], gv[ITG];
+#pragma unroll
+    for (int it = 0; it < ITU; ++it) {
+      const int i = threadIdx.x + it * DW_THREADS;
+      const int r = i >> 3, v = i & 7;
+      const int t = t0 - HALO + r;
+      uv[it] = make_uint4(0, 0, 0, 0);
+      if (r < ROWS && t >= 0 && t < T) uv[it] = *reinterpret_cast<const uint4*>(u + ((long long)b * T + t) * d + c0 + v * 8);
+    }
+#pragma unroll
+    for (int it = 0; it < ITG; ++it) {
+      const int i = threadIdx.x + it * DW_THREADS;
       const int r = i >> 3, v = i & 7;
       const int t = t0 + r;
-      uint4 val = make_uint4(0, 0, 0, 0);
-      if (t < T) val = *reinterpret_cast<const uint4*>(dwv + ((long long)b * T + t) * d + c0 + v * 8);
-      *reinterpret_cast<uint4*>(&gtile[r][v * 4]) = val;
+      gv[it] = make_uint4(0, 0, 0, 0);
+      if (t < T) gv[it] = *reinterpret_cast<const uint4*>(dwv + ((long long)b * T + t) * d + c0 + v * 8);
+    }
+#pragma unroll
+    for (int it = 0; it < ITU; ++it) {
+      const int i = threadIdx.x + it * DW_THREADS;
+      if (i < NU) {
+        float4* dst = reinterpret_cast<float4*>(&utile[i >> 3][(i & 7) * 4]);
+        const float2 p0 = unpack_bf16x2(uv[it].x), p1 = unpack_bf16x2(uv[it].y), p2 = unpack_bf16x2(uv[it].z), p3 = unpack_bf16x2(uv[it].w);
+        dst[0] = make_float4(p0.x, p0.y, p1.x, p1.y);
+        dst[1] = make_float4(p2.x, p2.y, p3.x, p3.y);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < ITG; ++it) {
+      const int i = threadIdx.x + it * DW_THREADS;
+      float4* dst = reinterpret_cast<float4*>(&gtile[i >> 3][(i & 7) * 4]);
+      const float2 p0 = unpack_bf16x2(gv[it].x), p1 = unpack_bf16x2(gv[it].y), p2 = unpack_bf16x2(gv[it].z), p3 = unpack_bf16x2(gv[it].w);
+      dst[0] = make_float4(p0.x, p0.y, p1.x, p1.y);
+      dst[1] = make_float4(p2.x, p2.y, p3.x, p3.y);
     }
     __syncthreads();
     // u row for (t, tap) is t + tap (the tile starts at t0 - 15)
-    float2 win[4];
+    const int tb = th * (TT / 2);
+    float2 win[WG_TAPS];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) win[k + 1] = __bfloat1622float2(utile[tap0 + k][lane]);
+    for (int k = 0; k < WG_TAPS - 1; ++k) win[k + 1] = utile[tb + tap0 + k][lane];
 #pragma unroll 8
-    for (int t = 0; t < TT; ++t) {
-      win[0] = win[1]; win[1] = win[2]; win[2] = win[3];
-      const int r = min(t + tap0 + 3, ROWS - 1);
-      win[3] = __bfloat1622float2(utile[r][lane]);
-      const float2 g = __bfloat1622float2(gtile[t][lane]);
+    for (int t = tb; t < tb + TT / 2; ++t) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        acc[k].x = fmaf(g.x, win[k].x, acc[k].x);
-        acc[k].y = fmaf(g.y, win[k].y, acc[k].y);
-      }
-      if (w == 7) { gsum.x += g.x; gsum.y += g.y; }
+      for (int k = 0; k < WG_TAPS - 1; ++k) win[k] = win[k + 1];
+      win[WG_TAPS - 1] = utile[t + tap0 + WG_TAPS - 1][lane];  // <= row ROWS (the zero row) for the last tap group
+      const float2 g = gtile[t][lane];
+#pragma unroll
+      for (int k = 0; k < WG_TAPS; ++k) acc[k] = __ffma2_rn(g, win[k], acc[k]);
+      if (tg == 0) gsum = __fadd2_rn(gsum, g);
     }
   }
+  // reduce: the two time halves through shared memory, then the CTAs of the cluster (neighbouring utterances, same
+  // channels) through distributed shared memory; each CTA of the cluster adds its share of the 64 x 32 sums (31 taps +
+  // bias) to global memory, so the number of same-address atomics drops by the cluster size.
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(dsm);  // [2][CC][32]
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < WG_TAPS; ++k) {
     const int tap = tap0 + k;
     if (tap < KW) {
-      atomicAdd(dweight + (long long)ch * KW + tap, acc[k].x);
-      atomicAdd(dweight + (long long)(ch + 1) * KW + tap, acc[k].y);
+      red[(th * CC + 2 * lane) * 32 + tap] = acc[k].x;
+      red[(th * CC + 2 * lane + 1) * 32 + tap] = acc[k].y;
     }
   }
-  if (w == 7 && dbias != nullptr) {
-    atomicAdd(dbias + ch, gsum.x);
-    atomicAdd(dbias + ch + 1, gsum.y);
+  if (tg == 0) {
+    red[(th * CC + 2 * lane) * 32 + 31] = gsum.x;
+    red[(th * CC + 2 * lane + 1) * 32 + 31] = gsum.y;
   }
+  cg::cluster_group cluster = cg::this_cluster();
+  cluster.sync();
+  const int csz = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+  const int per = (CC * 32) / csz;
+  for (int i = threadIdx.x; i < per; i += DW_THREADS) {
+    const int idx = crank * per + i;
+    float a = 0.f;
+    for (int r = 0; r < csz; ++r) {
+      const float* rp = cluster.map_shared_rank(red, r);
+      a += rp[idx] + rp[CC * 32 + idx];
+    }
+    const int c = idx >> 5, tap = idx & 31;
+    if (tap < KW) atomicAdd(dweight + (long long)(c0 + c) * KW + tap, a);
+    else if (dbias != nullptr) atomicAdd(dbias + c0 + c, a);
+  }
+  cluster.sync();  // keep every CTA's sums alive until its peers have read them
 }
 
 }  // namespace
@@ -213,12 +298,36 @@ extern "C" int tasr_dwconv31_bwd(const void* dw, const void* u, const void* ab, 
   dwconv_bwd_data_kernel<<<grid_a, DW_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dw), reinterpret_cast<const bf16*>(ab), T, d,
                                                         weight, reinterpret_cast<bf16*>(dab), reinterpret_cast<bf16*>(du));
   TASR_CHECK_LAUNCH();
-  int nseg = 592 / max(1, B * (d / CC));  // ~4 CTAs per SM, otherwise as few segments (= atomics) as possible
+  int nseg = 1184 / max(1, B * (d / CC));  // up to ~8 CTAs per SM of work, otherwise as few segments (= atomics) as possible
   nseg = max(1, min(nseg, ntiles));
   const int tiles_per_cta = cdiv(ntiles, nseg);
   dim3 grid_b(d / CC, cdiv(ntiles, tiles_per_cta), B);
-  dwconv_bwd_weight_kernel<<<grid_b, DW_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dw), reinterpret_cast<const bf16*>(u), T, d,
-                                                          dweight, dbias, tiles_per_cta);
+  constexpr int WSMEM = ((ROWS + 1) + TT) * (CC / 2) * (int)sizeof(float2);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM);
+    if (e != cudaSuccess) return tasr_set_cuda_error(e);
+    attr_done = true;
+  }
+  {
+    int cz = 8;
+    while (B % cz) cz >>= 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid_b;
+    cfg.blockDim = dim3(DW_THREADS);
+    cfg.dynamicSmemBytes = WSMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = cz;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, dwconv_bwd_weight_kernel, reinterpret_cast<const bf16*>(dw),
+                                       reinterpret_cast<const bf16*>(u), T, d, dweight, dbias, tiles_per_cta);
+    if (e != cudaSuccess) return tasr_set_cuda_error(e);
+  }
   TASR_CHECK_LAUNCH();
   return TASR_OK;
 }

@@ -262,24 +262,30 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int npart,
 }
 
 // s = silu((w - mean) * rstd * gamma + beta)
+// A thread owns 4 fixed channels (its constants live in registers) and walks rows.
 __global__ void __launch_bounds__(NT) bn_silu_apply_kernel(const bf16* __restrict__ w, long long M, int d,
                                                            const float* __restrict__ stats, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, bf16* __restrict__ out) {
-  const long long n4 = M * d / 4;
-  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
-    const int col = (int)((i * 4) % d);
-    float4 v = ld4_bf16(w + i * 4);
-    float4 st0 = ld4(stats + col * 2), st1 = ld4(stats + col * 2 + 4);  // (m0,r0,m1,r1),(m2,r2,m3,r3)
-    float4 ga = ld4(gamma + col), be = ld4(beta + col);
-    v.x = siluf_((v.x - st0.x) * st0.y * ga.x + be.x);
-    v.y = siluf_((v.y - st0.z) * st0.w * ga.y + be.y);
-    v.z = siluf_((v.z - st1.x) * st1.y * ga.z + be.z);
-    v.w = siluf_((v.w - st1.z) * st1.w * ga.w + be.w);
-    st4_bf16(out + i * 4, v);
+  const int tpr = d >> 2, rlanes = NT / tpr;
+  const int col = (threadIdx.x % tpr) << 2, rl = threadIdx.x / tpr;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float mean = stats[(col + j) * 2], rstd = stats[(col + j) * 2 + 1];
+    sc[j] = rstd * gamma[col + j];
+    sh[j] = beta[col + j] - mean * sc[j];
+  }
+  const long long stride = (long long)gridDim.x * rlanes;
+#pragma unroll 4
+  for (long long r = (long long)blockIdx.x * rlanes + rl; r < M; r += stride) {
+    float4 v = ld4_bf16(w + r * d + col);
+    v.x = silu_tanh(fmaf(v.x, sc[0], sh[0]));
+    v.y = silu_tanh(fmaf(v.y, sc[1], sh[1]));
+    v.z = silu_tanh(fmaf(v.z, sc[2], sh[2]));
+    v.w = silu_tanh(fmaf(v.w, sc[3], sh[3]));
+    st4_bf16(out + r * d + col, v);
   }
 }
-
-// backward pass 1: per-channel partial sums of dz*what and dz  (dz = ds * silu'(z))
 __global__ void __launch_bounds__(NT) bn_silu_bwd_stats_kernel(const bf16* __restrict__ ds, const bf16* __restrict__ w,
                                                                long long M, int d, int rows_per_cta,
                                                                const float* __restrict__ stats,
@@ -294,13 +300,14 @@ __global__ void __launch_bounds__(NT) bn_silu_bwd_stats_kernel(const bf16* __res
     ga[j] = gamma[col + j]; be[j] = beta[col + j];
   }
   float a[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+#pragma unroll 4
   for (long long r = r0 + rl; r < r1; r += rlanes) {
     float4 wv = ld4_bf16(w + r * d + col), dv = ld4_bf16(ds + r * d + col);
     const float wq[4] = {wv.x, wv.y, wv.z, wv.w}, dq[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float wh = (wq[j] - mean[j]) * rstd[j];
-      const float dz = dq[j] * silu_gradf_(wh * ga[j] + be[j]);
+      const float dz = dq[j] * silu_grad_tanh(wh * ga[j] + be[j]);
       a[j] += dz * wh;
       c[j] += dz;
     }
@@ -343,22 +350,30 @@ __global__ void __launch_bounds__(NT) bn_silu_bwd_apply_kernel(const bf16* __res
                                                                long long M, int d, const float* __restrict__ stats,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                const float* __restrict__ sums, bf16* __restrict__ dw) {
-  const long long n4 = M * d / 4;
+  const int tpr = d >> 2, rlanes = NT / tpr;
+  const int col = (threadIdx.x % tpr) << 2, rl = threadIdx.x / tpr;
   const float invM = 1.f / (float)M;
-  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
-    const int col = (int)((i * 4) % d);
-    float4 wv = ld4_bf16(w + i * 4), dv = ld4_bf16(ds + i * 4);
+  float mean[4], rstd[4], ga[4], be[4], c1[4], c2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mean[j] = stats[(col + j) * 2]; rstd[j] = stats[(col + j) * 2 + 1];
+    ga[j] = gamma[col + j]; be[j] = beta[col + j];
+    c2[j] = sums[(col + j) * 2] * invM;
+    c1[j] = sums[(col + j) * 2 + 1] * invM;
+  }
+  const long long stride = (long long)gridDim.x * rlanes;
+#pragma unroll 4
+  for (long long r = (long long)blockIdx.x * rlanes + rl; r < M; r += stride) {
+    const float4 wv = ld4_bf16(w + r * d + col), dv = ld4_bf16(ds + r * d + col);
     const float wq[4] = {wv.x, wv.y, wv.z, wv.w}, dq[4] = {dv.x, dv.y, dv.z, dv.w};
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float mean = stats[(col + j) * 2], rstd = stats[(col + j) * 2 + 1];
-      const float ga = gamma[col + j], be = beta[col + j];
-      const float wh = (wq[j] - mean) * rstd;
-      const float dz = dq[j] * silu_gradf_(wh * ga + be);
-      o[j] = ga * rstd * (dz - sums[(col + j) * 2 + 1] * invM - wh * sums[(col + j) * 2] * invM);
+      const float wh = (wq[j] - mean[j]) * rstd[j];
+      const float dz = dq[j] * silu_grad_tanh(fmaf(wh, ga[j], be[j]));
+      o[j] = ga[j] * rstd[j] * (dz - c1[j] - wh * c2[j]);
     }
-    st4_bf16(dw + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+    st4_bf16(dw + r * d + col, make_float4(o[0], o[1], o[2], o[3]));
   }
 }
 
@@ -647,8 +662,9 @@ extern "C" int tasr_bn_finalize(const float* partial, int npart, int d, int64_t 
 
 extern "C" int tasr_bn_silu_fwd(const void* w, int64_t M, int d, const float* stats, const float* gamma,
                                 const float* beta, void* out, tasr_stream_t stream) {
-  if (d % 4 || M <= 0) return TASR_ERR_SHAPE;
-  const int grid = (int)imin64((long long)148 * 8, (M * d / 4 + NT - 1) / NT);
+  const int tpr = d / 4;
+  if (d % 4 || tpr > NT || (NT % tpr) || M <= 0) return TASR_ERR_SHAPE;
+  const int grid = (int)imin64((long long)148 * 6, (M + (NT / tpr) - 1) / (NT / tpr));
   bn_silu_apply_kernel<<<grid, NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(w), M, d, stats, gamma, beta, reinterpret_cast<bf16*>(out));
   TASR_CHECK_LAUNCH();
@@ -678,7 +694,7 @@ extern "C" int tasr_bn_silu_bwd(const void* ds, const void* w, int64_t M, int d,
   TASR_CHECK_LAUNCH();
   bn_bwd_finalize_kernel<<<cdiv((long long)d * 32, 256), 256, 0, st>>>(partial, nparts, d, sums, dgamma, dbeta);
   TASR_CHECK_LAUNCH();
-  const int grid = (int)imin64((long long)148 * 8, (M * d / 4 + NT - 1) / NT);
+  const int grid = (int)imin64((long long)148 * 6, (M + (NT / tpr) - 1) / (NT / tpr));
   bn_silu_bwd_apply_kernel<<<grid, NT, 0, st>>>(reinterpret_cast<const bf16*>(ds), reinterpret_cast<const bf16*>(w), M, d,
                                                 stats, gamma, beta, sums, reinterpret_cast<bf16*>(dw));
   TASR_CHECK_LAUNCH();
