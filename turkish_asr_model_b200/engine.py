@@ -12,6 +12,8 @@ weights accumulated in fp32 straight into the flat gradient buffer by the split-
 """
 import math
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -144,6 +146,12 @@ class ConformerEngine:
         self.F2 = model.input_proj.in_features // self.d
         self._cos_sin = None
         self.device_seed = False  # True: dropout seeds come from the device counter (CUDA-graph replay)
+        # weight / bias gradient kernels are leaves of the backward graph: they run on a second (lower priority) stream
+        # and fill the SMs that the tail of each main-chain kernel leaves idle
+        self.overlap_wgrad = os.environ.get("TASR_NO_WGRAD_OVERLAP", "0") != "1"
+        self._side = None
+        self._side_busy = False
+        self._keep = []
 
     # ------------------------------------------------------------------ parameters
     def ensure_flat(self):
@@ -306,6 +314,44 @@ class ConformerEngine:
         return x5.view(M, d)
 
     # ------------------------------------------------------------------ backward
+    def ensure_side_stream(self, device):
+        """Create the side stream up front (must exist before a CUDA-graph capture starts)."""
+        if self.overlap_wgrad and (self._side is None or self._side.device != device):
+            self._side = torch.cuda.Stream(device=device, priority=0)
+        return self._side
+
+    def _leaf(self, fn, *tensors):
+        """Enqueue fn() (kernels nothing downstream in backward reads: weight / bias gradients) on the side stream,
+        ordered after what the current stream has enqueued so far.  `tensors` are kept alive until _join()."""
+        if not self.overlap_wgrad:
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        self.ensure_side_stream(main.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            fn()
+        self._side_busy = True
+        self._keep.extend(tensors)
+
+    def _join(self):
+        """The current stream waits for the side stream; only then may the tensors its kernels read be released."""
+        if self._side_busy:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_busy = False
+        self._keep.clear()
+
+    def _wgrad_bias(self, dy, x, out_f, in_f, tokens, gw, gb, remap=None):
+        """gw += dy^T x, gb += column sums of dy: leaf kernels (side stream)."""
+        def run():
+            self._wgrad(dy, x, out_f, in_f, tokens, gw, remap=remap)
+            L.colsum_add(dy, gb)
+        self._leaf(run, dy, x)
+
     def _wgrad(self, dy, x, out_f, in_f, tokens, gw, remap=None):
         """gw (out_f, in_f) fp32 += dy^T x."""
         p0, p1 = remap if remap is not None else (0, 0)
@@ -318,13 +364,11 @@ class ConformerEngine:
         d, dff = self.d, self.dff
         S, Gv = self.S, self.Gv
         gv, h = saved
-        self._wgrad(dy, h, d, dff, M, Gv(pre + "linear2.weight"))
-        L.colsum_add(dy, Gv(pre + "linear2.bias"))
+        self._wgrad_bias(dy, h, d, dff, M, Gv(pre + "linear2.weight"), Gv(pre + "linear2.bias"))
         dgv = torch.empty(M, 2 * dff, dtype=torch.bfloat16, device=dy.device)
         L.gemm(M, dff, d, dy, d, S(pre + "linear2.weight"), dff, L.EPI_SWIGLU_BWD, dgv, 2 * dff, b_mn=1, aux=gv,
                ldaux=2 * dff, n_half=dff, drop_p=drop, seed=seed)
-        self._wgrad(dgv, xn, 2 * dff, d, M, Gv(pre + "linear1.weight"))
-        L.colsum_add(dgv, Gv(pre + "linear1.bias"))
+        self._wgrad_bias(dgv, xn, 2 * dff, d, M, Gv(pre + "linear1.weight"), Gv(pre + "linear1.bias"))
         dxn = torch.empty(M, d, dtype=torch.bfloat16, device=dy.device)
         L.gemm(M, d, 2 * dff, dgv, 2 * dff, S(pre + "linear1.weight"), d, L.EPI_STORE, dxn, d, b_mn=1)
         return dxn
@@ -350,8 +394,8 @@ class ConformerEngine:
         dxn = self._ff_backward(pre + "ff2.", dy, sv["ff2"], sv["xn4"].view(M, d), M, drop, seed + 4)
         dy = gn_bwd(dxn, sv["x3"], sv["st4"], "norm_ff2.norm", True, cast=(1.0, 0.0, 0))
         # 3. conv module
-        self._wgrad(dy, sv["s"].view(M, d), d, d, M, Gv(pre + "conv.pointwise_conv2.weight", (d, d)))
-        L.colsum_add(dy, Gv(pre + "conv.pointwise_conv2.bias"))
+        self._wgrad_bias(dy, sv["s"].view(M, d), d, d, M, Gv(pre + "conv.pointwise_conv2.weight", (d, d)),
+                         Gv(pre + "conv.pointwise_conv2.bias"))
         ds = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
         L.gemm(M, d, d, dy, d, S(pre + "conv.pointwise_conv2.weight", (d, d)), d, L.EPI_STORE, ds, d, b_mn=1)
         dw = L.bn_silu_bwd(ds, sv["w"], sv["bnst"], P(pre + "conv.batch_norm.weight"), P(pre + "conv.batch_norm.bias"),
@@ -359,27 +403,28 @@ class ConformerEngine:
         dab = L.dwconv_bwd(dw.view(B, T, d), sv["u"].view(B, T, d), sv["ab"].view(B, T, 2 * d),
                            P(pre + "conv.depthwise_conv.weight", (d, 31)), Gv(pre + "conv.depthwise_conv.weight", (d, 31)),
                            Gv(pre + "conv.depthwise_conv.bias")).view(M, 2 * d)
-        self._wgrad(dab, sv["xn3"].view(M, d), 2 * d, d, M, Gv(pre + "conv.pointwise_conv1.weight", (2 * d, d)))
-        L.colsum_add(dab, Gv(pre + "conv.pointwise_conv1.bias"))
+        self._wgrad_bias(dab, sv["xn3"].view(M, d), 2 * d, d, M, Gv(pre + "conv.pointwise_conv1.weight", (2 * d, d)),
+                         Gv(pre + "conv.pointwise_conv1.bias"))
         dxn = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
         L.gemm(M, d, 2 * d, dab, 2 * d, S(pre + "conv.pointwise_conv1.weight", (2 * d, d)), d, L.EPI_STORE, dxn, d, b_mn=1)
         dy = gn_bwd(dxn, sv["x2"], sv["st3"], "conv.norm.norm", True, cast=(1.0, 0.0, 0))
         # 2. attention
-        self._wgrad(dy, sv["ctx"], d, d, M, Gv(pre + "attn.linear_out.weight"))
-        L.colsum_add(dy, Gv(pre + "attn.linear_out.bias"))
+        self._wgrad_bias(dy, sv["ctx"], d, d, M, Gv(pre + "attn.linear_out.weight"), Gv(pre + "attn.linear_out.bias"))
         dctx = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
         L.gemm(M, d, d, dy, d, S(pre + "attn.linear_out.weight"), d, L.EPI_STORE, dctx, d, b_mn=1)
         dqkv = L.mqa_bwd(sv["qkv"], sv["ctx"], dctx, sv["lse2"], B, T, H, d, key_len, cs, drop_p=drop, seed=seed + 2)
         nq = d + 2 * DH
-        self._wgrad(dqkv, sv["xn2"].view(M, d), nq, d, M, Gv(pre + "attn.linear_q.weight", self.qkv_w_shape))
-        L.colsum_add(dqkv, Gv(pre + "attn.linear_q.bias", (nq,)))
+        self._wgrad_bias(dqkv, sv["xn2"].view(M, d), nq, d, M, Gv(pre + "attn.linear_q.weight", self.qkv_w_shape),
+                         Gv(pre + "attn.linear_q.bias", (nq,)))
         dxn = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
         L.gemm(M, d, nq, dqkv, nq, S(pre + "attn.linear_q.weight", self.qkv_w_shape), d, L.EPI_STORE, dxn, d, b_mn=1)
         dy = gn_bwd(dxn, sv["x1"], sv["st2"], "norm_attn.norm", True, cast=(0.5, drop, seed + 0 + 1))
         # 1. ff1
         dxn = self._ff_backward(pre + "ff1.", dy, sv["ff1"], sv["xn1"].view(M, d), M, drop, seed + 0)
         # the gradient leaving block 0 feeds input_proj's backward GEMMs: emit its bf16 copy too
-        return gn_bwd(dxn, sv["x"], sv["st1"], "norm_ff1.norm", True, cast=(1.0, 0.0, 0) if i == 0 else None)
+        out = gn_bwd(dxn, sv["x"], sv["st1"], "norm_ff1.norm", True, cast=(1.0, 0.0, 0) if i == 0 else None)
+        self._join()  # this block's weight gradients are complete (and its temporaries may be released)
+        return out
 
     def backward(self, tape, dlogits, on_segment_done=None):
         """dlogits (B, T', V) bf16.  Accumulates (+=) every parameter gradient into flat.grads.
@@ -400,10 +445,10 @@ class ConformerEngine:
             dl = buf[:, :V]
         cs = self.cos_sin(T2, dev)
         # classifier (model/conformer.py:209)
-        self._wgrad(dl, tape["x_final_bf16"], V, d, M, Gv("fc.weight"))
-        L.colsum_add(dl, Gv("fc.bias"))
+        self._wgrad_bias(dl, tape["x_final_bf16"], V, d, M, Gv("fc.weight"), Gv("fc.bias"))
         dres = torch.empty(M, d, dtype=torch.float32, device=dev)
         L.gemm(M, d, V, dl, dl.stride(0), S("fc.weight"), d, L.EPI_STORE, dres, d, b_mn=1, out_f32=1)
+        self._join()
         if on_segment_done is not None:
             on_segment_done(0)
         dx0 = None
@@ -415,16 +460,18 @@ class ConformerEngine:
         if dx0 is None:  # no blocks
             dx0 = L.cast_bf16(dres)
         y2v = tape["y2"].view(M, F2 * d)
-        self._wgrad(dx0, y2v, d, F2 * d, M, Gv("input_proj.weight"), remap=(d, F2))
-        L.colsum_add(dx0, Gv("input_proj.bias"))
+        self._wgrad_bias(dx0, y2v, d, F2 * d, M, Gv("input_proj.weight"), Gv("input_proj.bias"), remap=(d, F2))
         Mpix = M * F2
         dz2 = torch.empty(Mpix, d, dtype=torch.bfloat16, device=dev)
         L.gemm(M, F2 * d, d, dx0, d, tape["winp"], F2 * d, L.EPI_SILU_BWD, dz2, F2 * d, b_mn=1, aux=tape["z2"],
                ldaux=F2 * d)
-        L.conv2_wgrad(dz2, tape["y1"], tape["T"], tape["F"], Gv("subsample.2.weight"))
-        L.colsum_add(dz2, Gv("subsample.2.bias"))
+        def conv2_leaf():
+            L.conv2_wgrad(dz2, tape["y1"], tape["T"], tape["F"], Gv("subsample.2.weight"))
+            L.colsum_add(dz2, Gv("subsample.2.bias"))
+        self._leaf(conv2_leaf, dz2)
         dy1 = L.conv2_dgrad(dz2, B, tape["T"], tape["F"], tape["w2p"])
         L.conv1_bwd(dy1, tape["feats"], P("subsample.0.weight"), P("subsample.0.bias"),
                     Gv("subsample.0.weight"), Gv("subsample.0.bias"))
+        self._join()
         if on_segment_done is not None:
             on_segment_done(1 + self.n_blocks)

@@ -218,6 +218,7 @@ class Trainer:
             # everything that is created lazily must exist before capture
             self.preprocessor._tables(dev)
             eng.cos_sin(4096, dev)
+            eng.ensure_side_stream(dev)
             L.workspace(1, dev)
             flat.refresh_shadow()
             eng.device_seed = True
@@ -225,7 +226,11 @@ class Trainer:
             g = torch.cuda.CUDAGraph()
             n0 = L.lib().tasr_launch_count()
             # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures
-            with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode="thread_local"):
+            # capture on a high-priority stream: the main chain's CTAs are scheduled ahead of the weight-gradient kernels
+            # that the engine runs on its (lowest-priority) side stream
+            if getattr(self, "_cap_stream", None) is None:
+                self._cap_stream = torch.cuda.Stream(device=dev, priority=-1)
+            with torch.cuda.graph(g, pool=self._graph_pool, stream=self._cap_stream, capture_error_mode="thread_local"):
                 feats, frames = self.preprocessor.extract_features_batch(s_w, st["n"], tmax)
                 loss = self._step_features(eng, flat, feats, s_t, frames, st["tl"], host_opt=False,
                                            device_opt=(self.world_size == 1))
