@@ -126,7 +126,7 @@ __device__ __forceinline__ void epilogue_bwd16(const GemmDev& p, int row, int co
   }
   if (EPI == TASR_EPI_SILU_BWD) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) lo[i] = lo[i] * silu_gradf_(bf16_at(x.a, i));
+    for (int i = 0; i < 16; ++i) lo[i] = lo[i] * silu_grad_tanh(bf16_at(x.a, i));
     return;
   }
 #pragma unroll
@@ -139,13 +139,15 @@ __device__ __forceinline__ void epilogue_bwd16(const GemmDev& p, int row, int co
       const float d = lo[k] * (j == 0 ? s0 : s1);
       const float g = bf16_at(x.a, k), v = bf16_at(x.b, k);
       if (EPI == TASR_EPI_SWIGLU_BWD) {
-        const float sg = sigmoidf_(g);
-        lo[k] = d * v * sg * (1.f + g * (1.f - sg));  // d/dg
-        hi[k] = d * g * sg;                            // d/dv
+        const float sg = sigmoid_tanh(g);
+        const float dsg = d * sg;
+        lo[k] = dsg * v * fmaf(g, 1.f - sg, 1.f);     // d/dg
+        hi[k] = dsg * g;                               // d/dv
       } else {
-        const float sv = sigmoidf_(v);
-        lo[k] = d * sv;                                // d/da
-        hi[k] = d * g * sv * (1.f - sv);               // d/db
+        const float sv = sigmoid_tanh(v);
+        const float dsv = d * sv;
+        lo[k] = dsv;                                   // d/da
+        hi[k] = dsv * g * (1.f - sv);                  // d/db
       }
     }
   }
@@ -239,8 +241,8 @@ __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col
     for (int i = 0; i < W; i += 2) {
       float s0 = 1.f, s1 = 1.f;
       if (p.drop_thresh) dropout_scale2_fast(dbase, dseed_hi, i >> 1, p.drop_thresh, p.drop_inv_keep, s0, s1);
-      const float v0 = (EPI == TASR_EPI_SWIGLU) ? siluf_(lo[i]) * hi[i] : lo[i] * sigmoidf_(hi[i]);
-      const float v1 = (EPI == TASR_EPI_SWIGLU) ? siluf_(lo[i + 1]) * hi[i + 1] : lo[i + 1] * sigmoidf_(hi[i + 1]);
+      const float v0 = (EPI == TASR_EPI_SWIGLU) ? silu_tanh(lo[i]) * hi[i] : lo[i] * sigmoid_tanh(hi[i]);
+      const float v1 = (EPI == TASR_EPI_SWIGLU) ? silu_tanh(lo[i + 1]) * hi[i + 1] : lo[i + 1] * sigmoid_tanh(hi[i + 1]);
       t3[i] = v0 * s0;
       t3[i + 1] = v1 * s1;
     }
@@ -249,7 +251,7 @@ __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col
 #pragma unroll
     for (int i = 0; i < W; ++i) {
       lo[i] = bf16_round(lo[i] + t3[i]);
-      t3[i] = siluf_(lo[i]);
+      t3[i] = silu_tanh(lo[i]);
     }
   } else if (EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) {
     const bf16* ax = reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux;
@@ -265,20 +267,22 @@ __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col
         const float d = lo[k] * (j == 0 ? s0 : s1);
         const float g = hi[k], v = t3[k];
         if (EPI == TASR_EPI_SWIGLU_BWD) {
-          const float sg = sigmoidf_(g);
-          lo[k] = d * v * sg * (1.f + g * (1.f - sg));  // d/dg
-          hi[k] = d * g * sg;                            // d/dv
+          const float sg = sigmoid_tanh(g);
+          const float dsg = d * sg;
+          lo[k] = dsg * v * fmaf(g, 1.f - sg, 1.f);     // d/dg
+          hi[k] = dsg * g;                               // d/dv
         } else {
-          const float sv = sigmoidf_(v);
-          lo[k] = d * sv;                                // d/da
-          hi[k] = d * g * sv * (1.f - sv);               // d/db
+          const float sv = sigmoid_tanh(v);
+          const float dsv = d * sv;
+          lo[k] = dsv;                                   // d/da
+          hi[k] = dsv * g * (1.f - sv);                  // d/db
         }
       }
     }
   } else if (EPI == TASR_EPI_SILU_BWD) {
     load_bf16_w<W>(reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux + col0, t3, nvalid);
 #pragma unroll
-    for (int i = 0; i < W; ++i) lo[i] = lo[i] * silu_gradf_(t3[i]);
+    for (int i = 0; i < W; ++i) lo[i] = lo[i] * silu_grad_tanh(t3[i]);
   } else if (EPI == TASR_EPI_ATOMIC) {
 #pragma unroll
     for (int i = 0; i < W; ++i) lo[i] *= p.alpha;
