@@ -385,7 +385,7 @@ constexpr int GN_CL = 8;
 constexpr long long GN_FUSED_MAX_SLICE = 8ll << 20;  // bytes of one utterance (T x d fp32) kept hot in L2 between the passes
 
 template <bool OUT_BF16>
-__global__ void __cluster_dims__(GN_CL, 1, 1) __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT)
 gn_fused_fwd_kernel(const float* __restrict__ x, int T, int d, int G, int rows_per_cta, float eps,
                     const float* __restrict__ gamma, const float* __restrict__ beta, void* __restrict__ out,
                     float* __restrict__ stats_out) {
@@ -393,7 +393,8 @@ gn_fused_fwd_kernel(const float* __restrict__ x, int T, int d, int G, int rows_p
   __shared__ float part[64][2];                          // this CTA's per-group (sum, sumsq)
   __shared__ float sh_s[NT], sh_ss[NT];
   __shared__ float sh_mean[64], sh_rstd[64];
-  const int b = blockIdx.x / GN_CL, rank = blockIdx.x % GN_CL;
+  const int ncl = (int)cluster.num_blocks();
+  const int b = blockIdx.x / ncl, rank = blockIdx.x % ncl;
   const int tpr = d >> 2, rlanes = NT / tpr;
   const int col = (threadIdx.x % tpr) << 2, rl = threadIdx.x / tpr;
   const int t0 = rank * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
@@ -422,7 +423,7 @@ gn_fused_fwd_kernel(const float* __restrict__ x, int T, int d, int G, int rows_p
   cluster.sync();
   if (threadIdx.x < G) {
     double a = 0.0, c = 0.0;
-    for (int r = 0; r < GN_CL; ++r) {
+    for (int r = 0; r < ncl; ++r) {
       const float* rp = cluster.map_shared_rank(&part[0][0], r);
       a += rp[threadIdx.x * 2];
       c += rp[threadIdx.x * 2 + 1];
@@ -458,7 +459,7 @@ gn_fused_fwd_kernel(const float* __restrict__ x, int T, int d, int G, int rows_p
 
 // backward: dx = rstd * (dy*gamma - S1/n - xhat*S2/n); per-channel sums of dy*xhat and dy exchanged through DSMEM
 template <bool DY_BF16>
-__global__ void __cluster_dims__(GN_CL, 1, 1) __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 2)
 gn_fused_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, int T, int d, int G, int rows_per_cta,
                     const float* __restrict__ stats, const float* __restrict__ gamma, float* __restrict__ dres,
                     int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta, bf16* __restrict__ cast_out,
@@ -467,7 +468,8 @@ gn_fused_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, in
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) float sh_dyn2[];
   // layout: part a (d) | part c (d) | tot a (d) | tot c (d) | S1 (G) | S2 (G)
-  const int b = blockIdx.x / GN_CL, rank = blockIdx.x % GN_CL;
+  const int ncl = (int)cluster.num_blocks();
+  const int b = blockIdx.x / ncl, rank = blockIdx.x % ncl;
   float* pa = sh_dyn2;
   float* pc = pa + d;
   float* ta = pc + d;
@@ -507,7 +509,7 @@ gn_fused_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, in
   cluster.sync();
   for (int ch = threadIdx.x; ch < d; ch += NT) {
     float av = 0.f, cv = 0.f;
-    for (int r = 0; r < GN_CL; ++r) {
+    for (int r = 0; r < ncl; ++r) {
       av += cluster.map_shared_rank(pa, r)[ch];
       cv += cluster.map_shared_rank(pc, r)[ch];
     }
@@ -562,6 +564,32 @@ gn_fused_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, in
   }
 }
 
+// cluster size: as many CTAs per utterance as keep the whole grid resident (ctas_per_sm CTAs fit an SM)
+int gn_cluster_size(int B, int T, int ctas_per_sm) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int cl = GN_CL;
+  while (cl > 1 && ((long long)B * cl > (long long)ctas_per_sm * sms || cl > T)) cl >>= 1;
+  return cl;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t gn_launch_cluster(void (*kern)(KArgs...), int B, int cl, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * cl);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 bool gn_shape_ok(int d, int G) {
   if (d <= 0 || G <= 0 || G > 64 || d % G) return false;
   const int cpg = d / G;
@@ -590,9 +618,11 @@ extern "C" int tasr_groupnorm_fwd(const float* x, int B, int T, int d, int G, fl
   if (workspace_bytes < tasr_groupnorm_workspace_bytes(B, T, d)) return TASR_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if ((long long)T * d * sizeof(float) <= GN_FUSED_MAX_SLICE) {  // one cluster per utterance; its slice is re-read through L2
-    const int frows = cdiv(T, GN_CL);
-    if (out_bf16) gn_fused_fwd_kernel<true><<<B * GN_CL, NT, 0, st>>>(x, T, d, G, frows, eps, gamma, beta, out, stats);
-    else gn_fused_fwd_kernel<false><<<B * GN_CL, NT, 0, st>>>(x, T, d, G, frows, eps, gamma, beta, out, stats);
+    const int cl = gn_cluster_size(B, T, 6);
+    const int frows = cdiv(T, cl);
+    cudaError_t e = out_bf16 ? gn_launch_cluster(gn_fused_fwd_kernel<true>, B, cl, 0, st, x, T, d, G, frows, eps, gamma, beta, out, stats)
+                             : gn_launch_cluster(gn_fused_fwd_kernel<false>, B, cl, 0, st, x, T, d, G, frows, eps, gamma, beta, out, stats);
+    if (e != cudaSuccess) return tasr_set_cuda_error(e);
     TASR_CHECK_LAUNCH();
     return TASR_OK;
   }
@@ -618,14 +648,15 @@ extern "C" int tasr_groupnorm_bwd(const void* dy, int dy_bf16, const float* x, i
   if (workspace_bytes < tasr_groupnorm_workspace_bytes(B, T, d)) return TASR_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if ((long long)T * d * sizeof(float) <= GN_FUSED_MAX_SLICE) {
-    const int frows = cdiv(T, GN_CL);
+    const int cl = gn_cluster_size(B, T, 2);
+    const int frows = cdiv(T, cl);
     const size_t fsm = ((size_t)4 * d + 2 * G) * sizeof(float);
-    if (dy_bf16)
-      gn_fused_bwd_kernel<true><<<B * GN_CL, NT, fsm, st>>>(dy, x, T, d, G, frows, stats, gamma, dres, accumulate, dgamma, dbeta,
-                                                           cout_, cast_alpha, cthresh, cinv, cast_seed, g_tasr_seed_ptr);
-    else
-      gn_fused_bwd_kernel<false><<<B * GN_CL, NT, fsm, st>>>(dy, x, T, d, G, frows, stats, gamma, dres, accumulate, dgamma, dbeta,
-                                                            cout_, cast_alpha, cthresh, cinv, cast_seed, g_tasr_seed_ptr);
+    const unsigned long long seed64 = cast_seed;
+    cudaError_t e = dy_bf16 ? gn_launch_cluster(gn_fused_bwd_kernel<true>, B, cl, fsm, st, dy, x, T, d, G, frows, stats, gamma, dres,
+                                                accumulate, dgamma, dbeta, cout_, cast_alpha, cthresh, cinv, seed64, g_tasr_seed_ptr)
+                            : gn_launch_cluster(gn_fused_bwd_kernel<false>, B, cl, fsm, st, dy, x, T, d, G, frows, stats, gamma, dres,
+                                                accumulate, dgamma, dbeta, cout_, cast_alpha, cthresh, cinv, seed64, g_tasr_seed_ptr);
+    if (e != cudaSuccess) return tasr_set_cuda_error(e);
     TASR_CHECK_LAUNCH();
     return TASR_OK;
   }
