@@ -39,6 +39,11 @@ def timeit(name, fn, bytes_=0, iters=10):
     print("%-28s %9.1f us   %7.2f TB/s (algorithmic %.1f MB)" % (name, us, bytes_ / us / 1e6 if bytes_ else 0, bytes_ / 1e6))
 
 
+from turkish_asr_model_b200.data.preprocessing import AudioPreprocessor  # noqa: E402
+_pre = AudioPreprocessor()
+_w = torch.randn(B, (T - 1) * 160, device=dev) * 0.1
+_n = torch.full((B,), (T - 1) * 160, dtype=torch.int64, device=dev)
+timeit("mel_forward", lambda: _pre.extract_features_batch(_w, _n, T), _w.numel() * 4 + B * T * F * 4 * 3)
 feats = torch.randn(B, T, F, device=dev)
 w1 = torch.randn(d, 1, 3, 3, device=dev) * 0.3
 b1 = torch.randn(d, device=dev) * 0.1

@@ -88,7 +88,8 @@ mel_logpower_kernel(const float* __restrict__ wave, long long wave_ld, const int
   float2* tw = reinterpret_cast<float2*>(win + NFFT);              // 400
   float2* Z = tw + NFFT;                                           // FR * ZLD
   float* P = reinterpret_cast<float*>(Z + FR * ZLD);               // FR * PLD
-  int* rng = reinterpret_cast<int*>(P + FR * PLD);                 // 2 * n_mels
+  int* rng = reinterpret_cast<int*>(P + FR * PLD);                 // 2 * 128
+  unsigned short* slot = reinterpret_cast<unsigned short*>(rng + 2 * 128);  // 200: where bin k of the 200-pt FFT was left
 
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FR;
@@ -98,22 +99,38 @@ mel_logpower_kernel(const float* __restrict__ wave, long long wave_ld, const int
   const int tid = threadIdx.x;
   const float* w = wave + (long long)b * wave_ld;
 
-  for (int i = tid; i < RAW; i += MEL_THREADS) {
-    int gi = HOP * t0 + i;  // index in the reflect-padded signal
-    float v = 0.f;
-    if (gi < N + NFFT) {
-      int j = gi - NFFT / 2;
-      if (j < 0) j = -j;
-      if (j >= N) j = 2 * (N - 1) - j;
-      v = w[j];
+  {
+    // all global loads are issued before the first shared-memory store (a load -> store loop with a run-time trip
+    // count exposes one DRAM round trip per iteration)
+    constexpr int IT = (RAW + MEL_THREADS - 1) / MEL_THREADS;
+    float v[IT];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int i = tid + it * MEL_THREADS;
+      const int gi = HOP * t0 + i;  // index in the reflect-padded signal
+      v[it] = 0.f;
+      if (i < RAW && gi < N + NFFT) {
+        int j = gi - NFFT / 2;
+        if (j < 0) j = -j;
+        if (j >= N) j = 2 * (N - 1) - j;
+        v[it] = w[j];
+      }
     }
-    raw[i] = v;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int i = tid + it * MEL_THREADS;
+      if (i < RAW) raw[i] = v[it];
+    }
   }
   for (int i = tid; i < NFFT; i += MEL_THREADS) {
     win[i] = window[i];
     tw[i] = g_tw400[i];
   }
   for (int i = tid; i < 2 * n_mels; i += MEL_THREADS) rng[i] = ranges[i];
+  for (int k = tid; k < 200; k += MEL_THREADS) {
+    const int k1 = k & 7, k2 = k >> 3;
+    slot[k] = (unsigned short)(25 * k1 + 5 * (k2 % 5) + k2 / 5);
+  }
   __syncthreads();
 
   // pass 1: radix-8 over n1 (n = 25 n1 + n2), twiddle W200^(n2 k1)
@@ -131,7 +148,7 @@ mel_logpower_kernel(const float* __restrict__ wave, long long wave_ld, const int
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) {
       float2 v = x[k1];
-      if (k1 > 0) v = cmul(v, tw[(2 * n2 * k1) % NFFT]);
+      if (k1 > 0) v = cmul(v, tw[2 * n2 * k1]);  // 2 n2 k1 <= 336 < 400
       z[25 * k1 + n2] = v;
     }
   }
@@ -148,7 +165,7 @@ mel_logpower_kernel(const float* __restrict__ wave, long long wave_ld, const int
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
       float2 v = x[c];
-      if (c > 0 && b5 > 0) v = cmul(v, tw[(16 * b5 * c) % NFFT]);
+      if (c > 0 && b5 > 0) v = cmul(v, tw[16 * b5 * c]);  // <= 256 < 400
       z[5 * c + b5] = v;
     }
   }
@@ -170,11 +187,9 @@ mel_logpower_kernel(const float* __restrict__ wave, long long wave_ld, const int
   for (int idx = tid; idx < FR * NBIN; idx += MEL_THREADS) {
     const int f = idx / NBIN, k = idx - f * NBIN;
     const float2* z = Z + f * ZLD;
-    const int ka = k % 200, kb = (200 - k) % 200;
-    int k1 = ka & 7, k2 = ka >> 3;
-    const float2 za = z[25 * k1 + 5 * (k2 % 5) + k2 / 5];
-    k1 = kb & 7; k2 = kb >> 3;
-    const float2 zb = z[25 * k1 + 5 * (k2 % 5) + k2 / 5];
+    const int ka = (k == 200) ? 0 : k, kb = (k == 0 || k == 200) ? 0 : 200 - k;
+    const float2 za = z[slot[ka]];
+    const float2 zb = z[slot[kb]];
     // E = (Za + conj(Zb))/2 ; O = (Za - conj(Zb))/(2i)
     const float er = 0.5f * (za.x + zb.x), ei = 0.5f * (za.y - zb.y);
     const float orr = 0.5f * (za.y + zb.y), oi = -0.5f * (za.x - zb.x);
@@ -235,27 +250,33 @@ __global__ void mel_cmvn_stats_kernel(const float* __restrict__ feats, const int
   }
 }
 
+// blockDim = (n_mels padded to 32, 8): x = bin (its mean / deviation are computed once per thread), y = frame lane
 __global__ void mel_cmvn_apply_kernel(float* __restrict__ feats, const int* __restrict__ n_samples, int Tmax,
                                       int n_mels, const int* __restrict__ utt_max, const double* __restrict__ stats,
-                                      int normalize) {
+                                      int normalize, int frames_per_cta) {
   const int b = blockIdx.y;
   const int T = 1 + n_samples[b] / HOP;
   const float cutoff = __int_as_float(utt_max[b]) - 200.f - 80.f;
-  const long long per_utt = (long long)Tmax * n_mels;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_utt; i += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(i / n_mels), m = (int)(i - (long long)t * n_mels);
-    float* p = feats + (long long)b * per_utt + i;
-    if (t >= T) {
-      *p = 0.f;
-      continue;
-    }
-    float v = fmaxf(*p, cutoff);
-    if (normalize) {
-      const double s = stats[((long long)b * n_mels + m) * 2], ss = stats[((long long)b * n_mels + m) * 2 + 1];
-      const double mean = s / T;
-      const double var = (ss - s * mean) / (double)(T - 1);  // unbiased; T == 1 -> NaN like the reference
-      const float sd = (float)sqrt(var > 0.0 ? var : (var == var ? 0.0 : var));
-      v = (v - (float)mean) / (sd + 1e-8f);
+  const int m = threadIdx.x;
+  if (m >= n_mels) return;
+  float mean_f = 0.f, den = 1.f;
+  if (normalize) {
+    const double s = stats[((long long)b * n_mels + m) * 2], ss = stats[((long long)b * n_mels + m) * 2 + 1];
+    const double mean = s / T;
+    const double var = (ss - s * mean) / (double)(T - 1);  // unbiased; T == 1 -> NaN like the reference
+    const float sd = (float)sqrt(var > 0.0 ? var : (var == var ? 0.0 : var));
+    mean_f = (float)mean;
+    den = sd + 1e-8f;
+  }
+  const int t_begin = blockIdx.x * frames_per_cta, t_end = min(Tmax, t_begin + frames_per_cta);
+  float* base = feats + (long long)b * Tmax * n_mels + m;
+#pragma unroll 4
+  for (int t = t_begin + threadIdx.y; t < t_end; t += blockDim.y) {
+    float* p = base + (long long)t * n_mels;
+    float v = 0.f;
+    if (t < T) {
+      v = fmaxf(*p, cutoff);
+      if (normalize) v = (v - mean_f) / den;
     }
     *p = v;
   }
@@ -297,7 +318,7 @@ extern "C" int tasr_mel_forward(const float* wave, int64_t wave_ld, const int32_
   cudaError_t e = cudaMemsetAsync(workspace, 0, tasr_mel_workspace_bytes(B, n_mels), st);
   if (e != cudaSuccess) return tasr_set_cuda_error(e);
 
-  const size_t smem = (size_t)RAW * 4 + NFFT * 4 + NFFT * 8 + (size_t)FR * ZLD * 8 + (size_t)FR * PLD * 4 + 2 * 128 * 4;
+  const size_t smem = (size_t)RAW * 4 + NFFT * 4 + NFFT * 8 + (size_t)FR * ZLD * 8 + (size_t)FR * PLD * 4 + 2 * 128 * 4 + 200 * 2 + 16;
   static bool attr_done = false;
   if (!attr_done) {
     e = cudaFuncSetAttribute(mel_logpower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -315,8 +336,10 @@ extern "C" int tasr_mel_forward(const float* wave, int64_t wave_ld, const int32_
     mel_cmvn_stats_kernel<<<g2, b2, 0, st>>>(feats, n_samples, Tmax, n_mels, utt_max, stats, fpc);
     TASR_CHECK_LAUNCH();
   }
-  dim3 g3(max(1, min(64, cdiv((long long)Tmax * n_mels, 256 * 4))), B);
-  mel_cmvn_apply_kernel<<<g3, 256, 0, st>>>(feats, n_samples, Tmax, n_mels, utt_max, stats, normalize);
+  const int fpa = 64;
+  dim3 g3(cdiv(Tmax, fpa), B);
+  dim3 b3(((n_mels + 31) / 32) * 32, 8);
+  mel_cmvn_apply_kernel<<<g3, b3, 0, st>>>(feats, n_samples, Tmax, n_mels, utt_max, stats, normalize, fpa);
   TASR_CHECK_LAUNCH();
   return TASR_OK;
 }
