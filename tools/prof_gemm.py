@@ -40,12 +40,11 @@ for name, fn in fns.items():
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 20
-    e0.record()
-    for _ in range(n):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / n * 1e3
+    n = 10
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:  # device time (python launch overhead excluded)
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+    us = sum(ev.device_time for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and "gemm" in ev.name) / n
     print("%-10s %8.1f us  %7.1f TFLOP/s" % (name, us, flops[name] / us / 1e6))

@@ -249,7 +249,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
               float y[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                v[i] = bf16_round(v[i] + p.bias[col0 + i]);
+                v[i] += p.bias[col0 + i];
                 y[i] = silu_tanh(v[i]);
               }
               stage_bf16_half(buf0, rloc, h, y);

@@ -244,8 +244,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int sub = 0; sub < 2; ++sub) preload_aux_bf16<EPI>(p, row, n0 + g * 64 + hsel * 32 + sub * 16, ax[sub]);
             }
           }
-          if (leader) bulk_wait_read<RINGG - NBUF>();
-          named_bar_sync(bar_id, G_SG_THREADS);
           uint8_t* buf0 = ring_base + (ring % RINGG) * STAGE_BYTES;
           uint8_t* buf1 = ring_base + ((ring + 1) % RINGG) * STAGE_BYTES;
           uint8_t* buf2 = ring_base + ((ring + 2) % RINGG) * STAGE_BYTES;
@@ -263,6 +261,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float t3[16];
             if (HAS_AUX_BF16) epilogue_bwd16<EPI>(p, row, col0, lo, hi, ax[sub]);
             else epilogue_math<EPI, 16>(p, row, col0, lo, hi, t3);
+            if (sub == 0) {
+              // the staging buffers are needed only now: the math above overlapped the TMA stores (their reads of
+              // these buffers) of the previous column group
+              if (leader) bulk_wait_read<RINGG - NBUF>();
+              named_bar_sync(bar_id, G_SG_THREADS);
+            }
             if (DUAL) {
               stage_bf16_16(buf0, rloc, chunk0, t3);
               stage_bf16_16(buf1, rloc, chunk0, lo);

@@ -89,7 +89,6 @@ __device__ __forceinline__ void load_bias_w(const float* __restrict__ bias, int 
     for (int i = 0; i < W; ++i) b[i] = (i < nvalid) ? bias[col0 + i] : 0.f;
   }
 }
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 // ------------------------------------------------------------------------------------------------
 // Operand pre-loading for the epilogues that read a saved tensor (16-column pieces).  The loads are issued before
@@ -233,10 +232,10 @@ __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col
   } else if (EPI == TASR_EPI_SWIGLU || EPI == TASR_EPI_GLU) {
     load_bias_w<W>(p.bias, col0, nvalid, t3);
 #pragma unroll
-    for (int i = 0; i < W; ++i) lo[i] = bf16_round(lo[i] + t3[i]);
+    for (int i = 0; i < W; ++i) lo[i] += t3[i];
     load_bias_w<W>(p.bias ? p.bias + p.n_half : nullptr, col0, nvalid, t3);
 #pragma unroll
-    for (int i = 0; i < W; ++i) hi[i] = bf16_round(hi[i] + t3[i]);
+    for (int i = 0; i < W; ++i) hi[i] += t3[i];
 #pragma unroll
     for (int i = 0; i < W; i += 2) {
       float s0 = 1.f, s1 = 1.f;
@@ -250,7 +249,7 @@ __device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col
     load_bias_w<W>(p.bias, col0, nvalid, t3);
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-      lo[i] = bf16_round(lo[i] + t3[i]);
+      lo[i] += t3[i];
       t3[i] = silu_tanh(lo[i]);
     }
   } else if (EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) {
