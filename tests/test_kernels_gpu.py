@@ -27,7 +27,7 @@ def bf(x):
 
 
 # ------------------------------------------------------------------ GroupNorm
-@pytest.mark.parametrize("B,T,d", [(3, 251, 256), (2, 126, 512), (1, 7, 256)])
+@pytest.mark.parametrize("B,T,d", [(3, 251, 256), (2, 126, 512), (1, 7, 256), (16, 45, 256)])
 @pytest.mark.parametrize("out_bf16", [True, False])
 def test_groupnorm_fwd_bwd(cuda, B, T, d, out_bf16):
     g = torch.Generator().manual_seed(B * 100 + T)
@@ -66,7 +66,7 @@ def test_groupnorm_fwd_bwd(cuda, B, T, d, out_bf16):
 
 
 # ------------------------------------------------------------------ depthwise conv + BatchNorm + SiLU
-@pytest.mark.parametrize("B,T,d", [(3, 251, 256), (2, 70, 512), (1, 5, 256)])
+@pytest.mark.parametrize("B,T,d", [(3, 251, 256), (2, 70, 512), (1, 5, 256), (16, 140, 256), (12, 33, 128)])
 def test_dwconv_bn_silu(cuda, B, T, d):
     g = torch.Generator().manual_seed(T)
     ab = bf(torch.randn(B, T, 2 * d, generator=g))

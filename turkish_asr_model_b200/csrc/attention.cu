@@ -53,18 +53,11 @@ __device__ __forceinline__ void store_tile_chunk(uint8_t* tile, int r, int c0, c
 }
 
 // dropout index space: element (b, h, q, key) -> ((b H + h) T + q) * even(T) + key, so (key, key + 1) pairs share a hash
-// Dropout mask of one (key, key + 1) pair inside a 32-key chunk: the chunk's hash base is computed once
-// (tasr_hash_pair_base of the chunk's first pair), pair j of the chunk costs one add + the mixer.  Forward and backward
-// walk the same 32-key chunks, so they see the same mask.  thresh_hi = thresh16 << 16.
-__device__ __forceinline__ void attn_drop_pair(uint32_t base32, uint32_t seed_hi, uint32_t j, uint32_t thresh_hi, bool& keep0,
-                                               bool& keep1) {
-  uint32_t x = base32 + j;
-  x ^= x >> 16; x *= 0x7FEB352Du;
-  x ^= seed_hi;
-  x ^= x >> 15; x *= 0x846CA68Bu;
-  x ^= x >> 16;
-  keep0 = (x << 16) >= thresh_hi;  // low 16-bit lane >= thresh16
-  keep1 = x >= thresh_hi;          // high 16-bit lane >= thresh16
+// Dropout mask of one (key, key + 1) pair inside a 32-key chunk: the chunk's affine hash part is computed once
+// (tasr_hash_pair_base_s32 of the chunk's first pair), pair j of the chunk costs one add + the mixer.  Forward and
+// backward walk the same 32-key chunks, so they see the same mask.  thresh_hi = thresh16 << 16.
+__device__ __forceinline__ void attn_drop_pair(uint32_t base32, uint32_t j, uint32_t thresh_hi, bool& keep0, bool& keep1) {
+  dropout_keep2_fast(base32, j, thresh_hi, keep0, keep1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -127,7 +120,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) mqa_fwd_kernel(const __grid_co
     load_v(0);
   }
   const unsigned long long dseed = (p.drop_thresh && p.seed_ptr) ? p.seed + *p.seed_ptr : p.seed;
-  const uint32_t dseed_hi = (uint32_t)(dseed >> 32), thresh_hi = p.drop_thresh << 16;
+  const uint32_t dseed32 = tasr_seed_mix(dseed), thresh_hi = p.drop_thresh << 16;
   const float scale2 = p.scale * LOG2E;
   float m_run = -INFINITY, l_part = 0.f;
   float o[32];
@@ -189,7 +182,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) mqa_fwd_kernel(const __grid_co
       tmem_ld32(tS + lane_addr + c * 32, u);
       tmem_ld_wait();
       float pv[32];
-      const uint32_t dbase = tasr_hash_pair_base(dseed, (drow + (unsigned long long)(j * BKV + c * 32)) >> 1);
+      const uint32_t dbase = tasr_hash_pair_base_s32(dseed32, (drow + (unsigned long long)(j * BKV + c * 32)) >> 1);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         float e0 = fast_exp2(fmaf(__uint_as_float(u[i]), scale2, -m_new));
@@ -201,7 +194,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) mqa_fwd_kernel(const __grid_co
         lsum += e0 + e1;
         if (p.drop_thresh) {
           bool k0, k1;
-          attn_drop_pair(dbase, dseed_hi, (uint32_t)(i >> 1), thresh_hi, k0, k1);
+          attn_drop_pair(dbase, (uint32_t)(i >> 1), thresh_hi, k0, k1);
           e0 = k0 ? e0 * p.drop_inv_keep : 0.f;
           e1 = k1 ? e1 * p.drop_inv_keep : 0.f;
         }
@@ -374,7 +367,7 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS) mqa_bwd_kernel(const __grid_c
   const int n = (int)(u_end - u_begin);
 
   const unsigned long long dseed = (p.drop_thresh && p.seed_ptr) ? p.seed + *p.seed_ptr : p.seed;
-  const uint32_t dseed_hi = (uint32_t)(dseed >> 32), thresh_hi = p.drop_thresh << 16;
+  const uint32_t dseed32 = tasr_seed_mix(dseed), thresh_hi = p.drop_thresh << 16;
   const float scale2 = p.scale * LOG2E;
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);     // Q K^T, dO V^T
   constexpr uint32_t idesc_t = umma_idesc_bf16(128, DH, 1, 1);      // P^T dO, dS^T Q
@@ -461,13 +454,13 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS) mqa_bwd_kernel(const __grid_c
         tmem_ld32(tDP + lane_addr + c * 32, ud);
         tmem_ld_wait();
         float pv[32], dsv[32];
-        const uint32_t dbase = tasr_hash_pair_base(dseed, (drow + (unsigned long long)(k0 + c * 32)) >> 1);
+        const uint32_t dbase = tasr_hash_pair_base_s32(dseed32, (drow + (unsigned long long)(k0 + c * 32)) >> 1);
         const int nvalid = Lk - k0 - c * 32;  // keys of this chunk that exist
         const float inv_keep = p.drop_thresh ? p.drop_inv_keep : 1.f;
 #pragma unroll
         for (int i2 = 0; i2 < 32; i2 += 2) {
           bool keep0 = true, keep1 = true;
-          if (p.drop_thresh) attn_drop_pair(dbase, dseed_hi, (uint32_t)(i2 >> 1), thresh_hi, keep0, keep1);
+          if (p.drop_thresh) attn_drop_pair(dbase, (uint32_t)(i2 >> 1), thresh_hi, keep0, keep1);
           float pr0 = fast_exp2(fmaf(__uint_as_float(us[i2]), scale2, -lse2));
           float pr1 = fast_exp2(fmaf(__uint_as_float(us[i2 + 1]), scale2, -lse2));
           if (nvalid < 32) {  // only in the last key block of an utterance

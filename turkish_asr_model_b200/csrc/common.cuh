@@ -97,16 +97,38 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 
 // Counter-based dropout mask, evaluated identically in forward and backward (no mask is stored).
-// One 32-bit hash serves TWO neighbouring elements (16-bit lanes): element idx is kept iff
-//   lane16(hash(seed, idx >> 1), idx & 1) >= thresh16,  thresh16 = round(p * 65536).
-__host__ __device__ __forceinline__ uint32_t tasr_hash_pair(unsigned long long seed, unsigned long long pair_idx) {
-  uint32_t x = (uint32_t)pair_idx + (uint32_t)seed;
-  x += (uint32_t)(pair_idx >> 32) * 0x9E3779B1u;
-  x ^= x >> 16; x *= 0x7FEB352Du;
-  x ^= (uint32_t)(seed >> 32);
-  x ^= x >> 15; x *= 0x846CA68Bu;
+// One hash serves TWO neighbouring elements: with x0 = lo32(pair) + hi32(pair) * GOLD and s32 = a 32-bit digest of the
+// 64-bit seed,
+//   t = x0 * C1 + s32;  t ^= t >> 15;  t *= C2;   lane1 = t >> 16,  lane0 = (t * GOLD) >> 16
+// and element idx is kept iff lane(idx & 1) >= thresh16 = round(p * 65536).  For a run of pairs the affine part is
+// computed once (base = x0 * C1 + s32) and pair j costs: one add (base + j * C1), the xorshift, two multiplies and
+// two compares (lane >= thresh16  <=>  word >= thresh16 << 16).
+#define TASR_HASH_C1 0x7FEB352Du
+#define TASR_HASH_C2 0x846CA68Bu
+#define TASR_HASH_GOLD 0x9E3779B1u
+__host__ __device__ __forceinline__ uint32_t tasr_seed_mix(unsigned long long seed) {
+  uint32_t x = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
+  x ^= x >> 16; x *= TASR_HASH_C1;
+  x ^= x >> 15; x *= TASR_HASH_C2;
   x ^= x >> 16;
   return x;
+}
+// affine part of the hash of pair `pair0` (pair0 + j follows by adding j * C1 as long as lo32 does not wrap)
+__host__ __device__ __forceinline__ uint32_t tasr_hash_pair_base_s32(uint32_t s32, unsigned long long pair0) {
+  return ((uint32_t)pair0 + (uint32_t)(pair0 >> 32) * TASR_HASH_GOLD) * TASR_HASH_C1 + s32;
+}
+__host__ __device__ __forceinline__ uint32_t tasr_hash_pair_base(unsigned long long seed, unsigned long long pair0) {
+  return tasr_hash_pair_base_s32(tasr_seed_mix(seed), pair0);
+}
+__host__ __device__ __forceinline__ uint32_t tasr_hash_finish(uint32_t t) {
+  t ^= t >> 15;
+  t *= TASR_HASH_C2;
+  return t;
+}
+// both 16-bit lanes packed: lane0 in the low half, lane1 in the high half
+__host__ __device__ __forceinline__ uint32_t tasr_hash_pair(unsigned long long seed, unsigned long long pair_idx) {
+  const uint32_t t = tasr_hash_finish(tasr_hash_pair_base(seed, pair_idx));
+  return (t & 0xFFFF0000u) | ((t * TASR_HASH_GOLD) >> 16);
 }
 __host__ __device__ __forceinline__ uint32_t tasr_drop_thresh16(float p) {
   if (!(p > 0.f)) return 0u;
@@ -123,20 +145,18 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned
   const uint32_t lane = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
   return lane >= thresh16 ? inv_keep : 0.f;
 }
-// fast path for a run of pairs that does not cross a 2^32 boundary: `base32` = lo32(pair0) + lo32(seed) +
-// hi32(pair0) * 0x9E3779B1 is computed once, pair j of the run costs one add + the mixer
-__host__ __device__ __forceinline__ uint32_t tasr_hash_pair_base(unsigned long long seed, unsigned long long pair0) {
-  return (uint32_t)pair0 + (uint32_t)seed + (uint32_t)(pair0 >> 32) * 0x9E3779B1u;
+// pair j of a run whose affine part is `base32` (tasr_hash_pair_base of the run's first pair)
+__device__ __forceinline__ void dropout_keep2_fast(uint32_t base32, uint32_t j, uint32_t thresh_hi, bool& keep0, bool& keep1) {
+  const uint32_t t = tasr_hash_finish(base32 + j * TASR_HASH_C1);
+  keep1 = t >= thresh_hi;                    // thresh_hi = thresh16 << 16
+  keep0 = t * TASR_HASH_GOLD >= thresh_hi;
 }
-__device__ __forceinline__ void dropout_scale2_fast(uint32_t base32, uint32_t seed_hi, uint32_t j, uint32_t thresh16,
+__device__ __forceinline__ void dropout_scale2_fast(uint32_t base32, uint32_t /*unused*/, uint32_t j, uint32_t thresh16,
                                                     float inv_keep, float& s0, float& s1) {
-  uint32_t x = base32 + j;
-  x ^= x >> 16; x *= 0x7FEB352Du;
-  x ^= seed_hi;
-  x ^= x >> 15; x *= 0x846CA68Bu;
-  x ^= x >> 16;
-  s0 = (x & 0xFFFFu) >= thresh16 ? inv_keep : 0.f;
-  s1 = (x >> 16) >= thresh16 ? inv_keep : 0.f;
+  bool k0, k1;
+  dropout_keep2_fast(base32, j, thresh16 << 16, k0, k1);
+  s0 = k0 ? inv_keep : 0.f;
+  s1 = k1 ? inv_keep : 0.f;
 }
 // both elements of the pair (idx even, idx + 1) with one hash
 __device__ __forceinline__ void dropout_scale2(unsigned long long seed, unsigned long long idx_even, uint32_t thresh16,

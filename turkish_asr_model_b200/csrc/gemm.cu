@@ -158,6 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool f32_out = F32_MODE || (EPI == TASR_EPI_STORE && p.out_f32);
     const bool direct_atomic = (EPI == TASR_EPI_ATOMIC) && (p.remap_p0 > 0);
     uint32_t tcount = 0, ring = 0;
+    const uint32_t s32 = gemm_drop_seed32(p);  // dropout seed digest, once per thread
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int n_tile = tile % p.tiles_n;
       const int m_tile = (tile / p.tiles_n) % p.tiles_m;
@@ -200,10 +201,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tmem_ld_wait();
               float* lo = reinterpret_cast<float*>(lo_u);
               if (EPI == TASR_EPI_RESID) {
-                epilogue_resid16(p, row, col0, lo, res[u]);
+                epilogue_resid16(p, s32, row, col0, lo, res[u]);
               } else {
                 float t3[16];
-                epilogue_math<EPI, 16>(p, row, col0, lo, lo, t3);
+                epilogue_math<EPI, 16>(p, s32, row, col0, lo, lo, t3);
               }
               if (direct_atomic) {
                 if (row < p.M) {
@@ -259,8 +260,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* lo = reinterpret_cast<float*>(lo_u);
             float* hi = reinterpret_cast<float*>(hi_u);
             float t3[16];
-            if (HAS_AUX_BF16) epilogue_bwd16<EPI>(p, row, col0, lo, hi, ax[sub]);
-            else epilogue_math<EPI, 16>(p, row, col0, lo, hi, t3);
+            if (HAS_AUX_BF16) epilogue_bwd16<EPI>(p, s32, row, col0, lo, hi, ax[sub]);
+            else epilogue_math<EPI, 16>(p, s32, row, col0, lo, hi, t3);
             if (sub == 0) {
               // the staging buffers are needed only now: the math above overlapped the TMA stores (their reads of
               // these buffers) of the previous column group
@@ -346,15 +347,15 @@ __global__ void gemm_debug_kernel(const bf16* A, long long lda, int a_mn, const 
     hi[i] = s1;
   }
   switch (p.epi) {
-    case TASR_EPI_STORE: epilogue_math<TASR_EPI_STORE, 16>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_RESID: epilogue_math<TASR_EPI_RESID, 16>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_SWIGLU: epilogue_math<TASR_EPI_SWIGLU, 16>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_GLU: epilogue_math<TASR_EPI_GLU, 16>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_SILU: epilogue_math<TASR_EPI_SILU, 16>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_SWIGLU_BWD: epilogue_math<TASR_EPI_SWIGLU_BWD, 16>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_GLU_BWD: epilogue_math<TASR_EPI_GLU_BWD, 16>(p, row, col0, lo, hi, t3); break;
-    case TASR_EPI_SILU_BWD: epilogue_math<TASR_EPI_SILU_BWD, 16>(p, row, col0, lo, hi, t3); break;
-    default: epilogue_math<TASR_EPI_ATOMIC, 16>(p, row, col0, lo, hi, t3); break;
+    case TASR_EPI_STORE: epilogue_math<TASR_EPI_STORE, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
+    case TASR_EPI_RESID: epilogue_math<TASR_EPI_RESID, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
+    case TASR_EPI_SWIGLU: epilogue_math<TASR_EPI_SWIGLU, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
+    case TASR_EPI_GLU: epilogue_math<TASR_EPI_GLU, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
+    case TASR_EPI_SILU: epilogue_math<TASR_EPI_SILU, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
+    case TASR_EPI_SWIGLU_BWD: epilogue_math<TASR_EPI_SWIGLU_BWD, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
+    case TASR_EPI_GLU_BWD: epilogue_math<TASR_EPI_GLU_BWD, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
+    case TASR_EPI_SILU_BWD: epilogue_math<TASR_EPI_SILU_BWD, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
+    default: epilogue_math<TASR_EPI_ATOMIC, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
   }
   const bool f32_out = (p.epi == TASR_EPI_RESID) || (p.epi == TASR_EPI_ATOMIC) || (p.epi == TASR_EPI_STORE && p.out_f32);
   for (int i = 0; i < 16; ++i) {

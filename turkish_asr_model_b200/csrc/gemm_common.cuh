@@ -94,6 +94,10 @@ __device__ __forceinline__ void load_bias_w(const float* __restrict__ bias, int 
 // Operand pre-loading for the epilogues that read a saved tensor (16-column pieces).  The loads are issued before
 // the thread waits for the accumulator / the staging barrier so that their (HBM) latency overlaps with those waits.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gemm_drop_seed32(const GemmDev& p) {
+  if (!p.drop_thresh) return 0u;
+  return tasr_seed_mix(p.seed_ptr ? p.seed + *p.seed_ptr : p.seed);
+}
 struct AuxBf16 {  // 16 bf16 of the first half (g | a | z) and 16 of the second half (v | b)
   uint4 a[2], b[2];
 };
@@ -116,13 +120,10 @@ __device__ __forceinline__ float bf16_at(const uint4* q, int k) {  // element k 
 }
 // math of the *_BWD epilogues on a pre-loaded piece: lo = accumulator in, lo/hi = outputs
 template <int EPI>
-__device__ __forceinline__ void epilogue_bwd16(const GemmDev& p, int row, int col0, float* lo, float* hi, const AuxBf16& x) {
-  uint32_t dbase = 0, dseed_hi = 0;
-  if (p.drop_thresh) {
-    const unsigned long long seed = p.seed_ptr ? p.seed + *p.seed_ptr : p.seed;
-    dbase = tasr_hash_pair_base(seed, (unsigned long long)((long long)row * p.N + col0) >> 1);
-    dseed_hi = (uint32_t)(seed >> 32);
-  }
+__device__ __forceinline__ void epilogue_bwd16(const GemmDev& p, uint32_t s32, int row, int col0, float* lo, float* hi, const AuxBf16& x) {
+  uint32_t dbase = 0;
+  const uint32_t dseed_hi = 0;
+  if (p.drop_thresh) dbase = tasr_hash_pair_base_s32(s32, (unsigned long long)((long long)row * p.N + col0) >> 1);
   if (EPI == TASR_EPI_SILU_BWD) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) lo[i] = lo[i] * silu_grad_tanh(bf16_at(x.a, i));
@@ -161,16 +162,13 @@ __device__ __forceinline__ void preload_aux_f32(const GemmDev& p, int row, int c
     x.v[0] = s[0]; x.v[1] = s[1]; x.v[2] = s[2]; x.v[3] = s[3];
   }
 }
-__device__ __forceinline__ void epilogue_resid16(const GemmDev& p, int row, int col0, float* lo, const AuxF32& x) {
+__device__ __forceinline__ void epilogue_resid16(const GemmDev& p, uint32_t s32, int row, int col0, float* lo, const AuxF32& x) {
   const int nvalid = (row < p.M) ? max(0, min(16, p.N - col0)) : 0;
   float bb[16];
   load_bias_w<16>(p.bias, col0, nvalid, bb);
-  uint32_t dbase = 0, dseed_hi = 0;
-  if (p.drop_thresh) {
-    const unsigned long long seed = p.seed_ptr ? p.seed + *p.seed_ptr : p.seed;
-    dbase = tasr_hash_pair_base(seed, (unsigned long long)((long long)row * p.N + col0) >> 1);
-    dseed_hi = (uint32_t)(seed >> 32);
-  }
+  uint32_t dbase = 0;
+  const uint32_t dseed_hi = 0;
+  if (p.drop_thresh) dbase = tasr_hash_pair_base_s32(s32, (unsigned long long)((long long)row * p.N + col0) >> 1);
   const float* res = reinterpret_cast<const float*>(x.v);
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
@@ -198,17 +196,14 @@ __device__ __forceinline__ void epilogue_resid16(const GemmDev& p, int row, int 
 // K = 256 GEMMs); W = 16 keeps the register footprint small enough for 16 epilogue warps per CTA.
 // ------------------------------------------------------------------------------------------------
 template <int EPI, int W>
-__device__ __forceinline__ void epilogue_math(const GemmDev& p, int row, int col0, float* lo, float* hi, float* t3) {
+__device__ __forceinline__ void epilogue_math(const GemmDev& p, uint32_t s32, int row, int col0, float* lo, float* hi, float* t3) {
   const int nvalid = (row < p.M) ? max(0, min(W, p.N - col0)) : 0;
   const long long r = row;
   // dropout: pair-hash over the run of W/2 pairs of this chunk (N % 32 == 0 is checked on the host, so a run never
-  // crosses a 2^32 boundary of the pair index)
-  uint32_t dbase = 0, dseed_hi = 0;
-  if (p.drop_thresh) {
-    const unsigned long long seed = p.seed_ptr ? p.seed + *p.seed_ptr : p.seed;
-    dbase = tasr_hash_pair_base(seed, (unsigned long long)(r * p.N + col0) >> 1);
-    dseed_hi = (uint32_t)(seed >> 32);
-  }
+  // crosses a 2^32 boundary of the pair index); s32 = tasr_seed_mix(seed), computed once per thread by the caller
+  uint32_t dbase = 0;
+  const uint32_t dseed_hi = 0;
+  if (p.drop_thresh) dbase = tasr_hash_pair_base_s32(s32, (unsigned long long)(r * p.N + col0) >> 1);
   if (EPI == TASR_EPI_STORE) {
     load_bias_w<W>(p.bias, col0, nvalid, t3);
 #pragma unroll
