@@ -18,10 +18,10 @@ M = B * Tp
 sel = sys.argv[1:]
 
 
-def timeit(name, fn, bytes_=0, iters=10):
+def timeit(name, fn, bytes_=0, iters=int(os.environ.get("BK_ITERS", "10"))):
     if sel and not any(s in name for s in sel):
         return
-    for _ in range(3):
+    for _ in range(int(os.environ.get("BK_WARMUP", "3"))):
         fn()
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:   # device time only (these calls are host-bound from python)
@@ -36,6 +36,9 @@ def timeit(name, fn, bytes_=0, iters=10):
         parts[k] = parts.get(k, 0.0) + ev.device_time / iters
     if len(parts) > 1:
         name = name + " [" + ", ".join("%s %.1f" % kv for kv in parts.items()) + "]"
+    if us <= 0:  # no CUPTI (e.g. running under ncu)
+        print("%-28s (no device timing available)" % name)
+        return
     print("%-28s %9.1f us   %7.2f TB/s (algorithmic %.1f MB)" % (name, us, bytes_ / us / 1e6 if bytes_ else 0, bytes_ / 1e6))
 
 
