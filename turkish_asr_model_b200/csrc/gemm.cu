@@ -538,9 +538,12 @@ inline bool use_wide(int M, int N, int splits) {
 
 template <int EPI, bool A_MN, bool B_MN>
 int launch_single(const tasr_gemm_args* a, GemmDev& p, cudaStream_t st) {
-  constexpr int R = (EPI == TASR_EPI_SILU || EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) ? 2 : 2;
-  if (use_wide(a->M, a->N, p.splits)) return launch_tc<EPI, 256, 3, R, A_MN, B_MN>(a, p, st);
-  return launch_tc<EPI, 128, 4, R, A_MN, B_MN>(a, p, st);
+  // split-K weight gradients stream two long operands and write one small tile at the end: a single staging buffer
+  // per epilogue group buys one more operand stage (deeper TMA look-ahead)
+  constexpr bool LONGK = (EPI == TASR_EPI_ATOMIC);
+  constexpr int R = LONGK ? 1 : 2;
+  if (use_wide(a->M, a->N, p.splits)) return launch_tc<EPI, 256, LONGK ? 4 : 3, R, A_MN, B_MN>(a, p, st);
+  return launch_tc<EPI, 128, LONGK ? 6 : 4, R, A_MN, B_MN>(a, p, st);
 }
 
 }  // namespace
@@ -556,7 +559,13 @@ extern "C" int tasr_gemm_bf16(const tasr_gemm_args* a, tasr_stream_t stream) {
   switch (a->epilogue) {
     case TASR_EPI_STORE:
       if (!am && !bm) return launch_single<TASR_EPI_STORE, false, false>(a, p, st);
-      if (!am && bm) return launch_single<TASR_EPI_STORE, false, true>(a, p, st);
+      if (!am && bm) {
+        // long reductions with a small output (FFN up-projection dgrad, K = 2 dff): MMA-bound, so trade the second
+        // staging buffer for two more operand stages
+        if (a->K >= 2048 && !a->out_f32 && !use_wide(a->M, a->N, p.splits))
+          return launch_tc<TASR_EPI_STORE, 128, 6, 1, false, true>(a, p, st);
+        return launch_single<TASR_EPI_STORE, false, true>(a, p, st);
+      }
       if (am && bm) return launch_single<TASR_EPI_STORE, true, true>(a, p, st);
       return launch_tc<TASR_EPI_STORE, 128, 4, 2, true, false>(a, p, st);
     case TASR_EPI_RESID:
