@@ -640,9 +640,18 @@ bool conv_shape_ok(int B, int T, int F, int d) {
 
 }  // namespace
 
+// tensor-core path (conv1_tc.cu): TASR_ERR_SHAPE when the shape is not covered
+int tasr_conv1_tc_fwd(const float* x, int B, int T, int F, int d, const float* w1, const float* b1, void* y1, cudaStream_t st);
+int tasr_conv1_tc_bwd(const void* dy1, const float* x, int B, int T, int F, int d, const float* w1, const float* b1,
+                      float* dw1, float* db1, cudaStream_t st);
+
 extern "C" int tasr_conv1_fwd(const float* x, int B, int T, int F, int d, const float* w1, const float* b1, void* y1,
                               tasr_stream_t stream) {
   if (d % 8 || d > 1024 || B <= 0 || T <= 0 || F <= 0) return TASR_ERR_SHAPE;
+  {
+    const int rc = tasr_conv1_tc_fwd(x, B, T, F, d, w1, b1, y1, reinterpret_cast<cudaStream_t>(stream));
+    if (rc != TASR_ERR_SHAPE) return rc;
+  }
   Geom g = geom(T, F);
   const int dpad = cdiv(d, 256) * 256;
   const int slices = cdiv(g.F1, PX) * (dpad / 256);
@@ -666,6 +675,10 @@ extern "C" int tasr_conv1_fwd(const float* x, int B, int T, int F, int d, const 
 extern "C" int tasr_conv1_bwd(const void* dy1, const float* x, int B, int T, int F, int d, const float* w1, const float* b1,
                               float* dw1, float* db1, tasr_stream_t stream) {
   if (d % 8 || d > 1024 || B <= 0 || T <= 0 || F <= 0) return TASR_ERR_SHAPE;
+  {
+    const int rc = tasr_conv1_tc_bwd(dy1, x, B, T, F, d, w1, b1, dw1, db1, reinterpret_cast<cudaStream_t>(stream));
+    if (rc != TASR_ERR_SHAPE) return rc;
+  }
   Geom g = geom(T, F);
   const int dpad = cdiv(d, 128) * 128;
   const int slices = cdiv(g.F1, PX) * (dpad / 128);
