@@ -66,38 +66,52 @@ __device__ __forceinline__ void build_weight_tile(uint8_t* sW, const float* __re
 
 // P tile of tile index `tile`: thread (pixel r = tid & 127, part = tid >> 7) writes taps 3 part .. 3 part + 2 (part < 3)
 // or the ones columns (part == 3).  Columns that are never written stay zero (the buffers are zeroed once).
-__device__ __forceinline__ void build_patch_tile(uint8_t* sP, const Conv1TcParams& p, int tile) {
+// Split in two so that the global loads of a tile are in flight while the previous tile is processed.
+struct PatchRegs {
+  float v[3];
+  bool valid;
+};
+__device__ __forceinline__ PatchRegs fetch_patch(const Conv1TcParams& p, int tile) {
+  PatchRegs pr;
+  pr.v[0] = pr.v[1] = pr.v[2] = 0.f;
   const int r = threadIdx.x & (TPIX - 1), part = threadIdx.x >> 7;
   const long long pix = (long long)tile * TPIX + r;
-  const bool valid = pix < p.npix;
+  pr.valid = tile < p.ntiles && pix < p.npix;
+  if (part == 3 || !pr.valid) return pr;
+  const long long bh = pix / p.F1;
+  const int w = (int)(pix - bh * p.F1);
+  const int b = (int)(bh / p.T1);
+  const int h = (int)(bh - (long long)b * p.T1);
+  const int tt = 2 * h - 1 + part;
+  if (tt < 0 || tt >= p.T) return pr;
+  const float* xr = p.x + ((long long)b * p.T + tt) * p.F;
+#pragma unroll
+  for (int kw = 0; kw < 3; ++kw) {
+    const int ff = 2 * w - 1 + kw;
+    if (ff >= 0 && ff < p.F) pr.v[kw] = xr[ff];
+  }
+  return pr;
+}
+__device__ __forceinline__ void store_patch(uint8_t* sP, const PatchRegs& pr) {
+  const int r = threadIdx.x & (TPIX - 1), part = threadIdx.x >> 7;
   if (part == 3) {
-    const bf16 one = __float2bfloat16(valid ? 1.f : 0.f);
+    const bf16 one = __float2bfloat16(pr.valid ? 1.f : 0.f);
     *reinterpret_cast<bf16*>(sP + sw128_off(r, 9)) = one;
     *reinterpret_cast<bf16*>(sP + sw128_off(r, 41)) = one;
     return;
   }
-  int b = 0, h = 0, w = 0;
-  if (valid) {
-    const long long bh = pix / p.F1;
-    w = (int)(pix - bh * p.F1);
-    b = (int)(bh / p.T1);
-    h = (int)(bh - (long long)b * p.T1);
-  }
-  const int kh = part;
-  const int tt = 2 * h - 1 + kh;
-  const bool rok = valid && tt >= 0 && tt < p.T;
-  const float* xr = p.x + ((long long)b * p.T + (rok ? tt : 0)) * p.F;
 #pragma unroll
   for (int kw = 0; kw < 3; ++kw) {
-    const int ff = 2 * w - 1 + kw;
-    const float v = (rok && ff >= 0 && ff < p.F) ? xr[ff] : 0.f;
     bf16 hi, lo;
-    split_bf16(v, hi, lo);
-    const int k = kh * 3 + kw;
+    split_bf16(pr.v[kw], hi, lo);
+    const int k = part * 3 + kw;
     *reinterpret_cast<bf16*>(sP + sw128_off(r, k)) = hi;
     *reinterpret_cast<bf16*>(sP + sw128_off(r, 16 + k)) = lo;
     *reinterpret_cast<bf16*>(sP + sw128_off(r, 32 + k)) = hi;
   }
+}
+__device__ __forceinline__ void build_patch_tile(uint8_t* sP, const Conv1TcParams& p, int tile) {
+  store_patch(sP, fetch_patch(p, tile));
 }
 
 // Z (128 x 256) = P Wt^T over K = 48 (three 16-wide steps), issued by one thread
@@ -142,6 +156,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_fwd_kernel(const __gri
   const int n = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
   if (n > 0) {
     build_patch_tile(sP, p, blockIdx.x);
+    if (n > 1) build_patch_tile(sP + P_BYTES, p, blockIdx.x + gridDim.x);
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -152,12 +167,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_fwd_kernel(const __gri
     for (int i = 0; i < n; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
       const int zb = i & 1;
-      // patch of the next tile (its buffer was read by the product of tile i-1, complete since the wait of iteration i-1)
-      if (i + 1 < n) build_patch_tile(sP + ((i + 1) & 1) * P_BYTES, p, tile + gridDim.x);
+      // input patch of tile i+2: its loads are in flight while tile i is processed (stored after the column loop)
+      const PatchRegs nxt = fetch_patch(p, (i + 2 < n) ? tile + 2 * (int)gridDim.x : p.ntiles);
       if (tid == 0) bulk_wait_read<0>();  // the stores of tile i-1 have read the staging tile
-      fence_proxy_async_smem();
       tc_fence_before();
-      __syncthreads();  // patch i+1 visible; everyone has drained Z buffer (i+1)&1 (tile i-1); staging free
+      __syncthreads();  // everyone has drained Z buffer (i+1)&1 (tile i-1); patch i+1 visible; staging free
       if (tid == 0 && i + 1 < n) {
         tc_fence_after();
         issue_gemm1(tmem + ((i + 1) & 1) * CD, sP + ((i + 1) & 1) * P_BYTES, sW);
@@ -185,8 +199,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_fwd_kernel(const __gri
         *reinterpret_cast<uint4*>(row + (((2 * c) ^ (rloc & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(row + (((2 * c + 1) ^ (rloc & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
+      if (i + 2 < n) store_patch(sP + zb * P_BYTES, nxt);  // buffer i&1: its product (tile i) is complete
       fence_proxy_async_smem();
-      __syncthreads();  // output tile staged
+      __syncthreads();  // output tile staged, patch i+2 written
       if (tid == 0) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) tma_store_2d(&tmY, sY + q * (TPIX * 128), q * 64, tile * TPIX);  // rows >= npix clipped
@@ -254,9 +269,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const Conv1
         g[0] = reinterpret_cast<const uint4*>(src)[0];
         g[1] = reinterpret_cast<const uint4*>(src)[1];
       }
+      // input patch of tile i+1: loads in flight while this tile is processed (stored after the column loop)
+      const PatchRegs nxt = fetch_patch(p, (i + 1 < n) ? tile + (int)gridDim.x : p.ntiles);
       // the dW / db product of tile i-1 has finished reading the dZ tile and patch buffer (i+1)&1
       if (i > 0) mbar_wait(&bars[1], ph ^ 1u);
-      if (i + 1 < n) build_patch_tile(sP + ((i + 1) & 1) * P_BYTES, p, tile + gridDim.x);
       mbar_wait(&bars[0], ph);
       __syncwarp();
       tc_fence_after();
@@ -293,6 +309,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const Conv1
         g[0] = gn[0];
         g[1] = gn[1];
       }
+      if (i + 1 < n) store_patch(sP + ((i + 1) & 1) * P_BYTES, nxt);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncthreads();  // Z drained, dZ tile and patch i+1 complete
