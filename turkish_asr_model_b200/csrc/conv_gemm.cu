@@ -37,8 +37,10 @@ struct ConvDev {
   float* dw;         // WGRAD: fp32 gradient (co, ci, 3, 3), accumulated
 };
 
-constexpr int CV_STAGES = 3;
-constexpr int CV_RINGG = 2;
+// forward stages two output tensors (z2, y2) per column group: 3 operand stages + 2 staging buffers per epilogue group;
+// dgrad / wgrad stage one: the second buffer is traded for a fourth operand stage (deeper TMA look-ahead)
+__host__ __device__ constexpr int cv_stages(int mode, int bn) { return (mode == 0 || bn < 256) ? 3 : 4; }
+__host__ __device__ constexpr int cv_ringg(int mode, int bn) { return (mode == 0 || bn < 256) ? 2 : 1; }
 
 template <int MODE, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -48,7 +50,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmY, const ConvDev p) {
   // cm0..3 : parity-class maps of y1 (FWD, WGRAD) or dy1 (DGRAD, output)      index = ph*2 + pw
   // tmW    : W2p (d, 9d) 2-D           tmZ : z2 (FWD out2) | dz2 (DGRAD/WGRAD in), 4-D     tmY : y2 (FWD out), 4-D
-  constexpr int STAGES = CV_STAGES;
+  constexpr int STAGES = cv_stages(MODE, BN);
+  constexpr int CV_RINGG = cv_ringg(MODE, BN);
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -615,6 +618,7 @@ int class_maps(CUtensorMap* cm, const void* base, int B, int T1, int F1, int d, 
 template <int MODE, int BN>
 int launch_conv(const CUtensorMap* cm, const CUtensorMap& tmW, const CUtensorMap& tmZ, const CUtensorMap& tmY, ConvDev& p,
                 cudaStream_t st) {
+  constexpr int CV_STAGES = cv_stages(MODE, BN), CV_RINGG = cv_ringg(MODE, BN);
   constexpr int SMEM = CV_STAGES * (BM * BK * 2 + BN * BK * 2) + 2 * CV_RINGG * STAGE_BYTES + (2 * CV_STAGES + 4) * 8 + 16 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget");
   auto kern = conv_gemm_kernel<MODE, BN>;
