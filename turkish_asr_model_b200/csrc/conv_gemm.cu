@@ -17,6 +17,7 @@
 //   WGRAD : dW2[co, ci, tap] += sum_pix dz2[pix, co] * y1[pix@tap, ci]               (split over pixel blocks)
 // The main loop / barrier / TMEM structure is the one of gemm.cu (persistent, warp-specialised, 2 accumulators).
 #include "gemm_common.cuh"
+#include <stdlib.h>
 #include <mutex>
 
 namespace {
@@ -42,7 +43,11 @@ struct ConvDev {
 __host__ __device__ constexpr int cv_stages(int mode, int bn) { return (mode == 0 || bn < 256) ? 3 : 4; }
 __host__ __device__ constexpr int cv_ringg(int mode, int bn) { return (mode == 0 || bn < 256) ? 2 : 1; }
 
-template <int MODE, int BN>
+// MC: the CTA pair (2k, 2k+1) is a cluster that walks neighbouring M tiles in lockstep (same N tile, same k-blocks);
+// each CTA fetches half of the weight (B) tile of a k-block and TMA-multicasts it to both, so the L2 -> shared-memory
+// traffic per k-block drops from 48 KB to 32 KB per SM (the main loop is operand-feed bound).  A stage is released to the
+// producers when BOTH CTAs' UMMAs have consumed it (multicast tcgen05.commit on the empty barriers).
+template <int MODE, int BN, bool MC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant__ CUtensorMap cm1,
                  const __grid_constant__ CUtensorMap cm2, const __grid_constant__ CUtensorMap cm3,
@@ -79,7 +84,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
     tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmY);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC ? 2 : 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -92,7 +97,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (MC) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast write
   grid_dependency_wait();  // prologue above overlaps the previous kernel's tail (PDL)
+  const int crank = MC ? (int)cluster_ctarank() : 0;
+  // MC: both CTAs of a pair run the same number of tiles; a pair whose second tile does not exist repeats the last
+  // tile (identical values are written twice)
+  const int tile_end = MC ? total_tiles + crank : total_tiles;
 
   auto class_map = [&](int idx) -> const CUtensorMap* {
     return idx == 0 ? &cm0 : (idx == 1 ? &cm1 : (idx == 2 ? &cm2 : &cm3));
@@ -102,7 +112,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile_raw = blockIdx.x; tile_raw < tile_end; tile_raw += gridDim.x) {
+        const int tile = min(tile_raw, total_tiles - 1);
         const int n_tile = tile % p.tiles_n;
         const int m_tile = (tile / p.tiles_n) % p.tiles_m;
         const int split = tile / (p.tiles_n * p.tiles_m);
@@ -112,7 +123,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+          mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);  // MC: half of B comes from the peer CTA
           uint8_t* a_dst = sA + s * A_BYTES;
           uint8_t* b_dst = sB + s * B_BYTES;
           if (MODE == CONV_FWD) {
@@ -125,8 +136,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
             const CUtensorMap* cm = class_map(((kh + 1) & 1) * 2 + ((kw + 1) & 1));
             tma_load_4d(a_dst, cm, &full_bar[s], c0, 4 * fblk - (kw == 0), 32 * tblk - (kh == 0), b);
             const int n0 = n_tile * BN;
+            if (MC) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmW, &full_bar[s], tap * p.d + c0, n0 + 64 * j);
+              for (int jj = 0; jj < BN / 128; ++jj) {
+                const int j = crank * (BN / 128) + jj;
+                tma_load_2d_mc(b_dst + j * 8192, &tmW, &full_bar[s], tap * p.d + c0, n0 + 64 * j, (uint16_t)3);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmW, &full_bar[s], tap * p.d + c0, n0 + 64 * j);
+            }
           } else if (MODE == CONV_DGRAD) {
             // M tile -> (b, iblk, jblk) of the parity class;  k-block -> (tap of the class, co chunk)
             const int jblk = m_tile % p.nf_blk;
@@ -138,8 +157,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
             // t' = i + (ph + 1 - kh) / 2  ->  +1 only for (ph = 1, kh = 0)
             tma_load_4d(a_dst, &tmZ, &full_bar[s], co0, 4 * jblk + (p.pw == 1 && kw == 0), 32 * iblk + (p.ph == 1 && kh == 0), b);
             const int n0 = n_tile * BN;
+            if (MC) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmW, &full_bar[s], tap * p.d + n0 + 64 * j, co0);
+              for (int jj = 0; jj < BN / 128; ++jj) {
+                const int j = crank * (BN / 128) + jj;
+                tma_load_2d_mc(b_dst + j * 8192, &tmW, &full_bar[s], tap * p.d + n0 + 64 * j, co0, (uint16_t)3);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmW, &full_bar[s], tap * p.d + n0 + 64 * j, co0);
+            }
           } else {
             // WGRAD: M tile -> co block, N tile -> (tap, ci block);  k-block -> pixel block (b, tblk16, fblk)
             const int fblk = kb % p.nf_blk;
@@ -164,7 +191,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      for (int tile_raw = blockIdx.x; tile_raw < tile_end; tile_raw += gridDim.x, ++tcount) {
+        const int tile = min(tile_raw, total_tiles - 1);
         const int split = tile / (p.tiles_n * p.tiles_m);
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
@@ -187,7 +215,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
                                         : umma_desc_sw128(b_base + k * 32, 16, 1024);
             umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          if (MC) umma_commit_mc(&empty_bar[s], (uint16_t)3);
+          else umma_commit(&empty_bar[s]);
         }
         umma_commit(&tfull_bar[acc]);
       }
@@ -202,7 +231,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
     const int bar_id = 1 + grp;
     uint8_t* ring_base = sC + grp * CV_RINGG * STAGE_BYTES;
     uint32_t tcount = 0, ring = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile_raw = blockIdx.x; tile_raw < tile_end; tile_raw += gridDim.x, ++tcount) {
+      const int tile = min(tile_raw, total_tiles - 1);
       const int n_tile = tile % p.tiles_n;
       const int m_tile = (tile / p.tiles_n) % p.tiles_m;
       const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
@@ -282,6 +312,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer may still multicast into this CTA's shared memory / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -621,16 +652,33 @@ int launch_conv(const CUtensorMap* cm, const CUtensorMap& tmW, const CUtensorMap
   constexpr int CV_STAGES = cv_stages(MODE, BN), CV_RINGG = cv_ringg(MODE, BN);
   constexpr int SMEM = CV_STAGES * (BM * BK * 2 + BN * BK * 2) + 2 * CV_RINGG * STAGE_BYTES + (2 * CV_STAGES + 4) * 8 + 16 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget");
-  auto kern = conv_gemm_kernel<MODE, BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (err != cudaSuccess) return tasr_set_cuda_error(err);
-    attr_done = true;
-  }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
-  const int grid = (int)(total < g_sms ? total : g_sms);
-  cudaError_t lerr = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)SMEM, st, cm[0], cm[1], cm[2], cm[3], tmW, tmZ, tmY, p);
+  cudaError_t lerr;
+  // forward / dgrad at full width: CTA pairs share the weight tile by TMA multicast (TASR_CONV_MC=0 disables)
+  static const bool mc_enabled = [] { const char* e = getenv("TASR_CONV_MC"); return !(e && e[0] == '0'); }();
+  if (MODE != CONV_WGRAD && BN == 256 && p.tiles_n == 1 && p.splits == 1 && total >= 2 && g_sms >= 2 && mc_enabled) {
+    auto kern = conv_gemm_kernel<MODE, BN, (MODE != CONV_WGRAD && BN == 256)>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+      if (err != cudaSuccess) return tasr_set_cuda_error(err);
+      attr_done = true;
+    }
+    const long long pairs = (total + 1) / 2;
+    const int grid = 2 * (int)(pairs < g_sms / 2 ? pairs : g_sms / 2);
+    lerr = launch_pdl_cluster(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)SMEM, st, 2, cm[0], cm[1], cm[2], cm[3], tmW, tmZ,
+                              tmY, p);
+  } else {
+    auto kern = conv_gemm_kernel<MODE, BN, false>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+      if (err != cudaSuccess) return tasr_set_cuda_error(err);
+      attr_done = true;
+    }
+    const int grid = (int)(total < g_sms ? total : g_sms);
+    lerr = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)SMEM, st, cm[0], cm[1], cm[2], cm[3], tmW, tmZ, tmY, p);
+  }
   if (lerr != cudaSuccess) return tasr_set_cuda_error(lerr);
   TASR_CHECK_LAUNCH();
   return TASR_OK;
