@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_fwd_kernel(const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;                       // 32 KB
   uint8_t* sP = smem + W_BYTES;             // 2 x 16 KB
-  uint8_t* sY = smem + W_BYTES + 2 * P_BYTES;  // 64 KB output staging: four [128 x 64] bf16 chunks (TMA store)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + DZ_BYTES);  // z0, z1
+  uint8_t* sY = smem + W_BYTES + 2 * P_BYTES;  // 2 x 64 KB output staging: four [128 x 64] bf16 chunks each (TMA store)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + 2 * DZ_BYTES);  // z0, z1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_fwd_kernel(const __gri
       const int zb = i & 1;
       // input patch of tile i+2: its loads are in flight while tile i is processed (stored after the column loop)
       const PatchRegs nxt = fetch_patch(p, (i + 2 < n) ? tile + 2 * (int)gridDim.x : p.ntiles);
-      if (tid == 0) bulk_wait_read<0>();  // the stores of tile i-1 have read the staging tile
+      if (tid == 0) bulk_wait_read<1>();  // the stores of tile i-2 have read their staging tile (two tiles alternate)
       tc_fence_before();
       __syncthreads();  // everyone has drained Z buffer (i+1)&1 (tile i-1); patch i+1 visible; staging free
       if (tid == 0 && i + 1 < n) {
@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_fwd_kernel(const __gri
       mbar_wait(&bars[zb], (uint32_t)(i >> 1) & 1u);
       __syncwarp();
       tc_fence_after();
-      uint8_t* row = sY + cq * (TPIX * 128) + rloc * 128;
+      uint8_t* sYt = sY + zb * DZ_BYTES;
+      uint8_t* row = sYt + cq * (TPIX * 128) + rloc * 128;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t u[16];
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_fwd_kernel(const __gri
       __syncthreads();  // output tile staged, patch i+2 written
       if (tid == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) tma_store_2d(&tmY, sY + q * (TPIX * 128), q * 64, tile * TPIX);  // rows >= npix clipped
+        for (int q = 0; q < 4; ++q) tma_store_2d(&tmY, sYt + q * (TPIX * 128), q * 64, tile * TPIX);  // rows >= npix clipped
         bulk_commit();
       }
     }
@@ -218,21 +219,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_fwd_kernel(const __gri
 // ------------------------------------------------------------------------------------------------
 // backward (weight and bias gradient)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const Conv1TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const Conv1TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;                                   // 32 KB
   uint8_t* sP = smem + W_BYTES;                         // 2 x 16 KB
   uint8_t* sDZ = smem + W_BYTES + 2 * P_BYTES;          // 64 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDZ + DZ_BYTES);  // z, d
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint8_t* sG = sDZ + DZ_BYTES;                         // 64 KB: dy1 tile (TMA, four [128 x 64] chunks)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + DZ_BYTES);  // z, d, g, (unused)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, cq = warp >> 2;
   const int rloc = quarter * 32 + lane;
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    tma_prefetch_desc(&tmG);
+    for (int q = 0; q < 4; ++q) mbar_init(&bars[q], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -242,6 +244,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const Conv1
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  auto load_dy = [&](int tile) {  // thread 0: the tile's 128 x 256 gradient block (rows >= npix zero-filled)
+    mbar_expect_tx(&bars[2], DZ_BYTES);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tma_load_2d(sG + q * (TPIX * 128), &tmG, &bars[2], q * 64, tile * TPIX);
+  };
   const uint32_t tZ = tmem, tD = tmem + CD;  // D: two accumulators (channel halves) of 32 columns
   const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
   constexpr uint32_t idesc2 = umma_idesc_bf16(128, 32, 1, 1);
@@ -252,6 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const Conv1
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
+      load_dy(blockIdx.x);
       tc_fence_after();
       issue_gemm1(tZ, sP, sW);
       umma_commit(&bars[0]);
@@ -262,12 +270,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const Conv1
       const uint32_t ph = (uint32_t)i & 1u;
       const long long pix = (long long)tile * TPIX + rloc;
       const bool pvalid = pix < p.npix;
-      const bf16* src = p.dy1 + pix * CD + cq * 64;
-      uint4 g[2];
-      g[0] = g[1] = make_uint4(0, 0, 0, 0);
-      if (pvalid) {
-        g[0] = reinterpret_cast<const uint4*>(src)[0];
-        g[1] = reinterpret_cast<const uint4*>(src)[1];
+      // this thread's 64 dy values of the tile: shared memory -> registers, then the buffer is refilled for tile i+1
+      (void)pvalid;
+      uint4 g[8];
+      {
+        mbar_wait(&bars[2], ph);
+        const uint8_t* grow = sG + cq * (TPIX * 128) + rloc * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g[q] = *reinterpret_cast<const uint4*>(grow + ((q ^ (rloc & 7)) << 4));
+        __syncthreads();
+        if (tid == 0 && i + 1 < n) {
+          fence_proxy_async_smem();
+          load_dy(tile + (int)gridDim.x);
+        }
       }
       // input patch of tile i+1: loads in flight while this tile is processed (stored after the column loop)
       const PatchRegs nxt = fetch_patch(p, (i + 1 < n) ? tile + (int)gridDim.x : p.ntiles);
@@ -281,13 +296,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const Conv1
         uint32_t u[16];
         tmem_ld16(tZ + lane_addr + cq * 64 + c * 16, u);
         tmem_ld_wait();
-        uint4 gn[2];
-        gn[0] = gn[1] = make_uint4(0, 0, 0, 0);
-        if (c < 3 && pvalid) {
-          gn[0] = reinterpret_cast<const uint4*>(src + (c + 1) * 16)[0];
-          gn[1] = reinterpret_cast<const uint4*>(src + (c + 1) * 16)[1];
-        }
-        const uint32_t gw[8] = {g[0].x, g[0].y, g[0].z, g[0].w, g[1].x, g[1].y, g[1].z, g[1].w};
+
+        const uint32_t gw[8] = {g[2 * c].x, g[2 * c].y, g[2 * c].z, g[2 * c].w, g[2 * c + 1].x, g[2 * c + 1].y, g[2 * c + 1].z, g[2 * c + 1].w};
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -306,8 +316,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const Conv1
         uint8_t* row = sDZ + cq * (TPIX * 128) + rloc * 128;
         *reinterpret_cast<uint4*>(row + (((2 * c) ^ (rloc & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(row + (((2 * c + 1) ^ (rloc & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        g[0] = gn[0];
-        g[1] = gn[1];
       }
       if (i + 1 < n) store_patch(sP + ((i + 1) & 1) * P_BYTES, nxt);
       tc_fence_before();
@@ -408,7 +416,7 @@ int tasr_conv1_tc_fwd(const float* x, int B, int T, int F, int d, const float* w
   if (reinterpret_cast<uintptr_t>(y1) & 15) return TASR_ERR_SHAPE;
   CUtensorMap tmY;
   if (make_out_map(&tmY, y1, p.npix) != TASR_OK) return TASR_ERR_CUDA;
-  constexpr int SMEM = W_BYTES + 2 * P_BYTES + DZ_BYTES + 64 + 1024;
+  constexpr int SMEM = W_BYTES + 2 * P_BYTES + 2 * DZ_BYTES + 64 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv1_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -428,7 +436,11 @@ int tasr_conv1_tc_bwd(const void* dy1, const float* x, int B, int T, int F, int 
   p.dy1 = reinterpret_cast<const bf16*>(dy1);
   p.dw1 = dw1;
   p.db1 = db1;
-  constexpr int SMEM = W_BYTES + 2 * P_BYTES + DZ_BYTES + 64 + 1024;
+  if (reinterpret_cast<uintptr_t>(dy1) & 15) return TASR_ERR_SHAPE;
+  CUtensorMap tmG;
+  if (make_out_map(&tmG, const_cast<void*>(dy1), p.npix) != TASR_OK) return TASR_ERR_CUDA;
+  constexpr int SMEM = W_BYTES + 2 * P_BYTES + 2 * DZ_BYTES + 64 + 1024;
+  static_assert(SMEM <= 232448, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv1_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -436,7 +448,7 @@ int tasr_conv1_tc_bwd(const void* dy1, const float* x, int B, int T, int F, int 
     attr_done = true;
   }
   const int grid = p.ntiles < tc_num_sms() ? p.ntiles : tc_num_sms();
-  conv1_tc_bwd_kernel<<<grid, TC_THREADS, SMEM, st>>>(p);
+  conv1_tc_bwd_kernel<<<grid, TC_THREADS, SMEM, st>>>(tmG, p);
   TASR_CHECK_LAUNCH();
   return TASR_OK;
 }
