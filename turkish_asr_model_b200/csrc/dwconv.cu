@@ -73,7 +73,7 @@ __device__ __forceinline__ void conv_strip(const bf162 (*tile)[CC / 2], int lane
 }
 
 // weight (d, 31) fp32 [reference layout (d,1,31)], bias (d)
-__global__ void __launch_bounds__(DW_THREADS, 2) dwconv_fwd_kernel(const bf16* __restrict__ u, int T, int d,
+__global__ void __launch_bounds__(DW_THREADS, 3) dwconv_fwd_kernel(const bf16* __restrict__ u, int T, int d,
                                                                    const float* __restrict__ weight,
                                                                    const float* __restrict__ bias, bf16* __restrict__ out,
                                                                    float* __restrict__ bn_partial) {
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dwconv_fwd_kernel(const bf16* _
 }
 
 // Backward, kernel A: du = corr(dw, flipped weight) with the GLU backward fused -> dab (M, 2d) (or du).
-__global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_data_kernel(const bf16* __restrict__ dwv, const bf16* __restrict__ ab,
+__global__ void __launch_bounds__(DW_THREADS, 3) dwconv_bwd_data_kernel(const bf16* __restrict__ dwv, const bf16* __restrict__ ab,
                                                                         int T, int d, const float* __restrict__ weight,
                                                                         bf16* __restrict__ dab, bf16* __restrict__ du_out) {
   __shared__ __align__(16) bf162 tile[ROWS][CC / 2];
