@@ -62,7 +62,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap cm0, const __grid_constant_
   constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr bool A_MN = (MODE == CONV_WGRAD);
   constexpr bool B_MN = (MODE != CONV_FWD);
-  constexpr int TROWS = (MODE == CONV_WGRAD) ? 16 : 32;  // time rows per TMA box (x4 frequency bins)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);

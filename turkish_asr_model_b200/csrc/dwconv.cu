@@ -172,7 +172,6 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_weight_kernel(const bf1
   float2 (*gtile)[CC / 2] = reinterpret_cast<float2 (*)[CC / 2]>(dsm + (ROWS + 1) * (CC / 2));  // [TT]
   const int c0 = blockIdx.x * CC, b = blockIdx.z;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int ch = c0 + 2 * lane;
   const int tg = w & 3, th = w >> 2;
   const int tap0 = WG_TAPS * tg;
   float2 acc[WG_TAPS];

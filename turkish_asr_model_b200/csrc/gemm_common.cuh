@@ -127,10 +127,9 @@ __device__ __forceinline__ void epilogue_bwd16(const GemmDev& p, uint32_t s32, i
   if (EPI == TASR_EPI_SILU_BWD) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) lo[i] = lo[i] * silu_grad_tanh(bf16_at(x.a, i));
-    return;
   }
 #pragma unroll
-  for (int i = 0; i < 16; i += 2) {
+  for (int i = 0; i < (EPI == TASR_EPI_SILU_BWD ? 0 : 16); i += 2) {
     float s0 = 1.f, s1 = 1.f;
     if (p.drop_thresh) dropout_scale2_fast(dbase, dseed_hi, i >> 1, p.drop_thresh, p.drop_inv_keep, s0, s1);
 #pragma unroll
