@@ -397,7 +397,7 @@ bool fill(Conv1TcParams* p, const float* x, int B, int T, int F, int d, const fl
   p->F1 = (F - 1) / 2 + 1;
   p->npix = (long long)B * p->T1 * p->F1;
   const long long nt = (p->npix + TPIX - 1) / TPIX;
-  if (nt > 0x3fffffffLL) return false;
+  if (p->npix > 0x7fffff00LL || nt > 0x3fffffffLL) return false;  // pixel rows are 32-bit TMA coordinates
   p->ntiles = (int)nt;
   p->w1 = w1; p->b1 = b1;
   p->y1 = nullptr; p->dy1 = nullptr; p->dw1 = nullptr; p->db1 = nullptr;
