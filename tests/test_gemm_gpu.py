@@ -97,3 +97,42 @@ def test_gemm_resid(cuda):
     torch.cuda.synchronize()
     ref = res.double().cpu() + 0.5 * (A.double().cpu() @ B.double().cpu().t() + bias.double().cpu())
     assert (out.double().cpu() - ref).abs().max().item() < 1e-3
+
+
+def test_dropout_mask_gemm_epilogues_match_cast_kernel(cuda):
+    """One dropout site = one mask over the flat element index: the forward GEMM epilogues (per-run fast hash), the
+    stand-alone / GroupNorm-backward cast (generic hash) and the SwiGLU backward epilogue must all see the same mask for
+    the same seed (forward RESID dropout is undone in backward by the cast; SwiGLU dropout by the SWIGLU_BWD epilogue)."""
+    M, N, K, p, seed = 300, 256, 64, 0.25, 777
+    g = torch.Generator().manual_seed(9)
+    A = torch.zeros(M, K, dtype=torch.bfloat16, device=cuda)
+    B = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16).to(cuda)
+    ones = torch.ones(N, device=cuda)
+    res = torch.zeros(M, N, device=cuda)
+    out = torch.empty(M, N, device=cuda)
+    L.gemm(M, N, K, A, K, B, K, L.EPI_RESID, out, N, bias=ones, aux=res, ldaux=N, alpha=1.0, drop_p=p, seed=seed)
+    cast = L.cast_bf16(torch.ones(M, N, device=cuda), alpha=1.0, drop_p=p, seed=seed)
+    torch.cuda.synchronize()
+    mask_gemm = out != 0
+    mask_cast = cast.float() != 0
+    assert torch.equal(mask_gemm, mask_cast)
+    keep = mask_gemm.float().mean().item()
+    assert abs(keep - (1 - p)) < 0.01
+    assert torch.allclose(out[mask_gemm], torch.full_like(out[mask_gemm], 1.0 / (1 - p)), rtol=1e-6)
+    # SwiGLU forward (dropout on the activation) vs SwiGLU backward epilogue (same mask applied to the incoming gradient)
+    dff = 128
+    W1 = torch.zeros(2 * dff, K, dtype=torch.bfloat16, device=cuda)
+    b1 = torch.cat([torch.full((dff,), 3.0), torch.full((dff,), 2.0)]).to(cuda)     # gate = 3, up = 2 everywhere
+    h = torch.empty(M, dff, dtype=torch.bfloat16, device=cuda)
+    gv = torch.empty(M, 2 * dff, dtype=torch.bfloat16, device=cuda)
+    L.gemm(M, dff, K, A, K, W1, K, L.EPI_SWIGLU, h, dff, out2=gv, ldo2=2 * dff, bias=b1, n_half=dff, drop_p=p, seed=seed + 1)
+    dy = torch.zeros(M, K, dtype=torch.bfloat16, device=cuda)
+    dy[:, 0] = 1.0
+    W2 = torch.zeros(K, dff, dtype=torch.bfloat16, device=cuda)
+    W2[0, :] = 1.0                                                                   # d act = 1 everywhere
+    dgv = torch.empty(M, 2 * dff, dtype=torch.bfloat16, device=cuda)
+    L.gemm(M, dff, K, dy, K, W2, dff, L.EPI_SWIGLU_BWD, dgv, 2 * dff, b_mn=1, aux=gv, ldaux=2 * dff, n_half=dff,
+           drop_p=p, seed=seed + 1)
+    torch.cuda.synchronize()
+    assert torch.equal(h.float() != 0, dgv[:, dff:].float() != 0)
+    assert abs((h.float() != 0).float().mean().item() - (1 - p)) < 0.01
