@@ -121,3 +121,24 @@ def test_oracle_vs_live_reference():
     sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
     with torch.no_grad():
         assert (ref(x, il) - oc.forward(x, il, sd, 4, 2, training=False)).abs().max().item() < 1e-5
+
+
+def test_ctc_oracle_vs_torch_ctc_loss():
+    """The fp64 CTC restatement (oracle/ctc.py) against torch's own CTCLoss + autograd on the CPU, i.e. exactly the
+    reference's call (trainer/trainer.py:76,167-173: log_softmax -> CTCLoss(blank=0, reduction='mean',
+    zero_infinity=True)), including repeated labels, a short input, an empty target and an infeasible sample."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    B, T, V, S = 5, 40, 17, 12
+    logits = torch.randn(B, T, V, generator=g, dtype=torch.float64, requires_grad=True)
+    targets = torch.randint(1, V, (B, S), generator=g)
+    targets[1, 3] = targets[1, 2]                      # repeated label (needs a blank in between)
+    tl = torch.tensor([12, 7, 0, 12, 3])
+    il = torch.tensor([40, 25, 10, 11, 40])            # sample 3: 12 labels in 11 frames -> infeasible -> 0 loss, 0 grad
+    lp = F.log_softmax(logits, dim=-1).transpose(0, 1)
+    ref = F.ctc_loss(lp, targets, il, tl, blank=0, reduction="mean", zero_infinity=True)
+    ref.backward()
+    loss, nll, grad = octc.ctc_loss_and_grad(logits.detach().numpy(), targets.numpy(), il.numpy(), tl.numpy())
+    assert abs(float(loss) - float(ref.detach())) < 1e-9
+    assert np.abs(grad - logits.grad.numpy()).max() < 1e-9
+    assert np.abs(grad[3]).max() == 0.0 and np.abs(grad[1, 25:]).max() == 0.0
