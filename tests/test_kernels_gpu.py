@@ -3,7 +3,6 @@
 Tolerances: bf16 outputs are compared at bf16 resolution (relative 2^-8 of the tensor scale);
 fp32 outputs at 1e-4..1e-5; CTC loss/gradient at the north_star's 1e-3 relative; integers bit-exact.
 """
-import math
 
 import numpy as np
 import pytest
