@@ -231,6 +231,8 @@ def run_gpu(args):
     class Cfg:
         log_interval = 10 ** 9
     trainer = Trainer(model, None, opt, sched, dev, Cfg(), None, gradient_clip=1.0, accumulation_steps=1)
+    if args.no_graphs:
+        trainer.use_cuda_graphs = False
 
     K, W = args.steps, args.warmup
     # every distinct batch shape is seen (and its CUDA graph captured) during warm-up
@@ -373,7 +375,7 @@ def run_gpu(args):
         gms = r0.elapsed_time(r1) / reps
         step_ms_this_batch = None
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        trainer.use_cuda_graphs = True
+        trainer.use_cuda_graphs = not args.no_graphs
         resident_step(0)
         s0.record()
         resident_step(0)
@@ -427,6 +429,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graphs", action="store_true",
+                    help="eager launches instead of per-shape CUDA graphs (under DP: bucketed all-reduce overlapped with backward)")
     ap.add_argument("--model", default="default", choices=["default", "conformer-m"],
                     help="default = BASELINE configs[1] (the headline); conformer-m = configs[2] (d_model 512, 8 heads, 16 blocks)")
     args = ap.parse_args()
