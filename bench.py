@@ -242,7 +242,8 @@ def run_gpu(args):
     for b in batches:
         dev_batches.append({"waves": synth_waves(b, dev), "n_samples": b["n_samples"].to(dev), "targets": b["targets"].to(dev),
                             "target_lengths": b["target_lengths"].to(dev), "tmax": 1 + int(b["n_samples"].max()) // 160,
-                            "audio_s": float(b["n_samples"].sum()) / SR})
+                            "audio_s": float(b["n_samples"].sum()) / SR,
+                            "padded_s": float(b["n_samples"].max()) * len(b["n_samples"]) / SR})
 
     def sync_all():
         torch.cuda.synchronize()
@@ -264,10 +265,12 @@ def run_gpu(args):
     launches0 = L.lib().tasr_launch_count() + trainer.graph_kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     audio = 0.0
+    padded = 0.0  # audio seconds including the zero padding to the longest utterance of each batch (what is computed)
     e0.record()
     for i in range(K):
         loss = resident_step(W + i)
         audio += dev_batches[(W + i) % n_distinct]["audio_s"]
+        padded += dev_batches[(W + i) % n_distinct]["padded_s"]
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
@@ -314,12 +317,12 @@ def run_gpu(args):
 
     # ---- max over ranks, sum of audio
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    a = torch.tensor([audio, audio_e2e], dtype=torch.float64, device=dev)
+    a = torch.tensor([audio, audio_e2e, padded], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(a, op=dist.ReduceOp.SUM)
     ms, ms_e2e = float(t[0]), float(t[1])
-    audio, audio_e2e = float(a[0]), float(a[1])
+    audio, audio_e2e, padded = float(a[0]), float(a[1]), float(a[2])
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM), CUDA events around each launch, rank 0
     roofline = None
@@ -416,6 +419,8 @@ def run_gpu(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "final_loss": final_loss,
+            # `value` counts real (unpadded) audio; the same run counted in padded seconds
+            "padded_audio_seconds_per_second": padded / (ms * 1e-3),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
