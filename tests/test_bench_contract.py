@@ -1,0 +1,22 @@
+"""The reference arm of bench.py runs on the CPU (oracle port of the reference): check the JSON contract the driver
+reads (one line, the tier's keys) without a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         check=True, capture_output=True, text=True, timeout=600, cwd=ROOT).stdout.strip().splitlines()
+    line = json.loads(out[-1])
+    assert line["impl"] == "reference"
+    assert line["metric"] == "train_audio_seconds_per_second" and line["unit"] == "audio-s/s"
+    assert line["higher_is_better"] is True and line["scaling"] == "weak" and line["vs_baseline"] is None
+    assert line["value"] > 0 and line["n_gpus"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
