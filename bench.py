@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """Headline benchmark: training audio-seconds/second of the waveform -> log-mel -> Conformer -> CTC
-(fwd + bwd + clip + AdamW) hot path, BASELINE.json config[1]:
+(fwd + bwd + clip + AdamW) hot path, BASELINE.json configs[1]:
 
     default Conformer-CTC (80 mel, d_model 256, 4 heads, 8 blocks, V = 1000), bf16 operands,
     batch 64 of bucketed 5-15 s synthetic 16 kHz utterances per GPU, dropout 0.1.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--model default|conformer-m] [--workload train|augment|infer60]
 
 One JSON line on stdout (rank 0).  `value` = real (unpadded) audio seconds of all ranks / device time of K
 steps with the waveforms already resident in HBM; `e2e` = the same through Trainer.train_step_waveforms with
 pinned HOST buffers (H2D of waveforms/targets/lengths and D2H of the loss inside the timed region).
-`--impl reference` times the CPU oracle port of the reference (oracle/, plain PyTorch on the host cores) on a
-bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, staged by oracle/install_ref.py: its own
+AudioPreprocessor, collate_fn, TurkishASRModel and Trainer.train_epoch) on the host cores, CUDA hidden, on a bounded
+sample of the same workload; when the staged reference is absent it falls back to the oracle port (oracle/).
+Other workloads (not the driver's headline): --model conformer-m = configs[2]; --workload augment = configs[4]
+(GPU SpeedPerturbation + SpecAugment in front of the step); --workload infer60 = configs[3] (32 x 60 s greedy decode).
 """
 import argparse
 import json
@@ -21,7 +25,10 @@ import sys
 import threading
 import time
 
-import torch
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1: sys.argv.index("--impl") + 2] == ["reference"]:
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""  # the reference arm is the reference's CPU path: hide the GPUs from torch
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -30,10 +37,19 @@ SR = 16000
 CFG = dict(n_mels=80, d_model=256, n_heads=4, n_blocks=8, vocab=1000, dropout=0.1, batch=64)
 METRIC = "train_audio_seconds_per_second"
 UNIT = "audio-s/s"
+SPEEDS = (0.9, 1.0, 1.1)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, workload="train"):
     name = "BASELINE configs[1]: default Conformer-CTC" if CFG["d_model"] == 256 else "BASELINE configs[2]: Conformer-M"
+    if workload == "augment":
+        name = "BASELINE configs[4]: augmented pipeline (SpeedPerturbation 0.9/1.0/1.1 + SpecAugment 2x27 freq, 2x100 time) on " + name
+    if workload == "infer60":
+        return {"workload": "BASELINE configs[3]: long-form inference, 32 x 60 s utterances, log-mel + encoder (padding mask) + "
+                            "greedy CTC decode to token ids, default Conformer-CTC (d_model=%d, %d blocks, V=1000), eval mode"
+                            % (CFG["d_model"], CFG["n_blocks"]),
+                "per_gpu_batch": 32, "global_batch": 32 * n_gpus, "utterance_seconds": 60, "parallelism": "dp%d" % n_gpus,
+                "l2": "every step streams 123 MB of waveforms and >1 GB of activations (>> 126 MB L2)"}
     return {
         "workload": "%s (80 mel, d_model=%d, %d heads, %d blocks, V=1000) full "
                     "training step (log-mel + fwd + CTC + bwd + clip + AdamW), batch 64 bucketed 5-15 s synthetic 16 kHz "
@@ -126,10 +142,64 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_step_fn(threads):
-    """The reference's CPU path restated by the oracle (plain PyTorch fp32 autograd on the host cores):
-    per-utterance log-mel (numpy), model forward, log_softmax + CTCLoss, backward, clip_grad_norm_, AdamW.
-    The oracle is only the thing being *timed* here (cpu_baseline / --impl reference), never the product."""
+def cpu_sample(batch, n_utts=8):
+    """Bounded sample of the workload: the first n_utts utterances of a bucketed batch."""
+    ns = batch["n_samples"][:n_utts]
+    g = torch.Generator().manual_seed(batch["seed"])
+    nmax = int(ns.max())
+    w = 0.1 * torch.randn(n_utts, nmax, generator=g)
+    tl = batch["target_lengths"][:n_utts]
+    targets = batch["targets"][:n_utts, : int(tl.max())]
+    return w, ns, targets, tl
+
+
+def reference_step_fn(threads):
+    """The UNMODIFIED reference from baseline/_ref through its own public API and stock code path:
+    AudioPreprocessor.extract_features per utterance (data/preprocessing.py:81-110, what ASRDataset.__getitem__ runs),
+    collate_fn (data/dataset.py:283-312), TurkishASRModel + Trainer.train_epoch over that batch
+    (trainer/trainer.py:147-225: forward, log_softmax, CTCLoss, backward, clip_grad_norm_, AdamW, OneCycleLR)."""
+    import types
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    sys.path.insert(0, ref_dir)
+    sys.modules.setdefault("jiwer", types.ModuleType("jiwer"))  # WER/CER dependency of utils/metrics.py, never called here
+    import warnings
+    warnings.filterwarnings("ignore")
+    from data.dataset import collate_fn
+    from data.preprocessing import AudioPreprocessor
+    from model.conformer import TurkishASRModel
+    from trainer.trainer import Trainer
+    assert os.path.realpath(sys.modules["model.conformer"].__file__).startswith(os.path.realpath(ref_dir))
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = TurkishASRModel(CFG["n_mels"], CFG["d_model"], CFG["n_heads"], CFG["n_blocks"], CFG["vocab"], dropout=CFG["dropout"])
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=1e-6)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=5e-4, total_steps=100000, pct_start=0.1, anneal_strategy="cos")
+
+    class _Log:
+        def info(self, *a, **k):
+            pass
+        warning = error = info
+
+    class _Cfg:
+        log_interval = 10 ** 9
+        epochs = 1
+    pre = AudioPreprocessor()
+    tr = Trainer(model, None, opt, sched, torch.device("cpu"), _Cfg(), _Log(), gradient_clip=1.0, accumulation_steps=1)
+
+    def step(waves, ns, targets, tl):
+        items = []
+        for b in range(waves.shape[0]):
+            feats = pre.extract_features(waves[b: b + 1, : int(ns[b])])
+            items.append((feats, targets[b, : int(tl[b])]))
+        tr.train_loader = [collate_fn(items)]
+        return float(tr.train_epoch(1))
+
+    return step, "reference"
+
+
+def port_step_fn(threads):
+    """Fallback when baseline/_ref is absent: the oracle port of the same path (plain PyTorch fp32 autograd on the host
+    cores; dropout not modelled).  The oracle is only the thing being *timed* here, never the product."""
     import numpy as np
     from oracle import conformer as oc
     from oracle import mel as om
@@ -155,22 +225,19 @@ def cpu_reference_step_fn(threads):
         opt.step()
         return float(loss.detach())
 
-    return step
+    return step, "port"
 
 
-def cpu_sample(batch, n_utts=8):
-    """Bounded sample of the workload: the first n_utts utterances of a bucketed batch."""
-    ns = batch["n_samples"][:n_utts]
-    g = torch.Generator().manual_seed(batch["seed"])
-    nmax = int(ns.max())
-    w = 0.1 * torch.randn(n_utts, nmax, generator=g)
-    tl = batch["target_lengths"][:n_utts]
-    targets = batch["targets"][:n_utts, : int(tl.max())]
-    return w, ns, targets, tl
-
-
-def time_cpu(steps, warmup, threads, batches):
-    step = cpu_reference_step_fn(threads)
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import install_ref
+    threads = os.cpu_count() or 1
+    step, kind = (reference_step_fn if install_ref.available() else port_step_fn)(threads)
+    batches = make_batches(4, 0, 1)
+    steps = max(1, min(args.steps, 3))
+    warmup = 1
     total_audio, total_t = 0.0, 0.0
     for i in range(warmup + steps):
         w, ns, targets, tl = cpu_sample(batches[i % len(batches)])
@@ -180,35 +247,149 @@ def time_cpu(steps, warmup, threads, batches):
         if i >= warmup:
             total_audio += float(ns.sum()) / SR
             total_t += dt
-    return total_audio / total_t, total_t / max(steps, 1)
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    threads = os.cpu_count() or 1
-    batches = make_batches(4, 0, 1)
-    steps = max(1, min(args.steps, 3))
-    warmup = 1
-    val, sec_per_step = time_cpu(steps, warmup, threads, batches)
+    val = total_audio / total_t
+    sample = ("first 8 utterances of each bucketed batch of 64 (5-15 s), full train step in fp32 on %d host threads: "
+              % threads)
+    sample += ("the unmodified reference (baseline/_ref): AudioPreprocessor.extract_features per utterance + collate_fn + "
+               "Trainer.train_epoch, dropout 0.1, CUDA hidden" if kind == "reference" else
+               "oracle port of the reference on torch CPU (baseline/_ref not staged; dropout not modelled, which favours the CPU arm)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": total_t / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "first 8 utterances of each bucketed batch of 64 (5-15 s), full train step, fp32, "
-                                   "oracle port of the reference on torch CPU (dropout not modelled: favours the CPU arm)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_subprocess():
+    """cpu_baseline of the GPU arm: the reference arm in a child process (its torch must not see the GPUs)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                           capture_output=True, text=True, timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                cb = d["cpu_baseline"]
+                cb["sample"] += ", %.2f s/step" % (d["ms_per_step"] / 1e3)
+                return cb
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:  # the GPU line is still valid without it
+        return {"error": repr(e)[:300]}
+
+
+# --------------------------------------------------------------------------------------------- per-family rooflines
+def _timed(fn, reps, flush):
+    """Mean device time (ms) of fn() over `reps` launches, CUDA events on the current stream around each launch,
+    L2 flushed (a 512 MB fill) between launches so that HBM-bound kernels see cold operands as they do inside a step."""
+    fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(reps):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    return total / reps
+
+
+def kernel_rooflines(model, batch, dev, peaks, traffic):
+    """One roofline entry per kernel family of the step, each op launched stand-alone at the shape of
+    `batch` (the longest bench batch) through the same C-ABI wrappers the engine uses; algorithmic work per launch as
+    stated in DESIGN.md §4; `traffic` = DRAM bytes per launch from the committed ncu capture (profiles/), if present."""
+    from turkish_asr_model_b200 import _lib as L
+    from turkish_asr_model_b200.data.preprocessing import AudioPreprocessor
+    hbm = float(peaks.get("hbm_gbs", 6550.0))
+    tens = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    eng = model.engine()
+    flat = eng.ensure_flat()
+    flat.refresh_shadow()
+    P, S = eng.P, eng.S
+    d, H, G, V = eng.d, eng.H, eng.G, eng.V
+    B = batch["waves"].shape[0]
+    T = batch["tmax"]
+    T1, F1, T2, F2 = L.sub_dims(T, 80)
+    M = B * T2
+    flush = torch.empty(128 << 20, dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev).manual_seed(7)
+    out = []
+
+    def entry(name, bound, work, ms, note=""):
+        ach = work / (ms * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+        peak = hbm if bound == "hbm" else tens
+        out.append({"kernel": name, "bound": bound, "work_per_launch": work, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                    "ms": ms, "achieved": ach, "peak": peak, "frac": ach / peak, "traffic": traffic.get(name), "note": note})
+
+    # ---- mel
+    pre = AudioPreprocessor(device="cuda")
+    ns = batch["n_samples"]
+    ms = _timed(lambda: pre.extract_features_batch(batch["waves"], ns, T), 5, flush)
+    feats, frames = pre.extract_features_batch(batch["waves"], ns, T)
+    entry("mel_forward", "hbm", float(ns.sum()) * 4 + float((1 + ns // 160).sum()) * 80 * 4, ms,
+          "logpower + cmvn stats + cmvn apply (3 launches); bytes = samples in + features out")
+    # ---- conv2 implicit GEMM (fwd / dgrad / wgrad)
+    w2p = L.pack_weight_remap(P("subsample.2.weight").view(d, 9 * d), 9)
+    y1 = L.conv1_fwd(feats, P("subsample.0.weight"), P("subsample.0.bias"))
+    fl = 2.0 * (M * F2) * d * 9 * d
+    entry("conv2_fwd", "tensor", fl, _timed(lambda: L.conv2_fwd(y1, T, 80, w2p, P("subsample.2.bias")), 5, flush))
+    z2, y2 = L.conv2_fwd(y1, T, 80, w2p, P("subsample.2.bias"))
+    dz2 = (0.01 * torch.randn(M * F2, d, device=dev, generator=g)).to(torch.bfloat16)
+    entry("conv2_dgrad", "tensor", fl, _timed(lambda: L.conv2_dgrad(dz2, B, T, 80, w2p), 5, flush))
+    gw2 = torch.zeros(d, d, 3, 3, device=dev)
+    entry("conv2_wgrad", "tensor", fl, _timed(lambda: L.conv2_wgrad(dz2, y1, T, 80, gw2), 5, flush))
+    del y1, z2, y2, dz2
+    # ---- GroupNorm
+    x = torch.randn(B, T2, d, device=dev, generator=g)
+    gam, bet = P("blocks.0.norm_ff1.norm.weight"), P("blocks.0.norm_ff1.norm.bias")
+    entry("groupnorm_fwd", "hbm", M * d * (4 + 2), _timed(lambda: L.groupnorm_fwd(x, G, gam, bet), 10, flush),
+          "fp32 in, bf16 out")
+    xn, st = L.groupnorm_fwd(x, G, gam, bet)
+    dyb = (0.01 * torch.randn(B, T2, d, device=dev, generator=g)).to(torch.bfloat16)
+    dres = torch.zeros(B, T2, d, device=dev)
+    dg, db = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    entry("groupnorm_bwd", "hbm", M * d * (2 + 4 + 4 + 4 + 2),
+          _timed(lambda: L.groupnorm_bwd(dyb, x, G, st, gam, dres, True, dg, db, cast=(1.0, 0.0, 0)), 10, flush),
+          "bf16 dy + fp32 x in, fp32 residual gradient read+write, bf16 operand copy out")
+    # ---- depthwise conv
+    u = (torch.randn(B, T2, d, device=dev, generator=g)).to(torch.bfloat16)
+    ww, wb = P("blocks.0.conv.depthwise_conv.weight", (d, 31)), P("blocks.0.conv.depthwise_conv.bias")
+    entry("dwconv31_fwd", "hbm", 2 * M * d * 2, _timed(lambda: L.dwconv_fwd(u, ww, wb, want_stats=True), 10, flush),
+          "bf16 in/out, BatchNorm partial sums fused")
+    ab = (torch.randn(B, T2, 2 * d, device=dev, generator=g)).to(torch.bfloat16)
+    gww, gwb = torch.zeros(d, 31, device=dev), torch.zeros(d, device=dev)
+    entry("dwconv31_bwd", "hbm", 6 * M * d * 2, _timed(lambda: L.dwconv_bwd(dyb, u, ab, ww, gww, gwb), 10, flush),
+          "data + weight kernels; reads dw, u, a|b, writes da|db")
+    # ---- attention
+    qkv = (torch.randn(M, d + 128, device=dev, generator=g)).to(torch.bfloat16)
+    key_len = (frames.to(dev) // 4).contiguous()
+    att_fl = float((4.0 * T2 * key_len.double() * d).sum())
+    entry("mqa_attention_fwd", "tensor", att_fl, _timed(lambda: L.mqa_fwd(qkv, B, T2, H, d, key_len, drop_p=0.1, seed=1), 5, flush),
+          "4*T'*L'*d flops per utterance")
+    ctx, lse2 = L.mqa_fwd(qkv, B, T2, H, d, key_len, drop_p=0.1, seed=1)
+    dctx = (0.01 * torch.randn(M, d, device=dev, generator=g)).to(torch.bfloat16)
+    cs = eng.cos_sin(T2, dev)
+    entry("mqa_attention_bwd", "tensor", 2.5 * att_fl,
+          _timed(lambda: L.mqa_bwd(qkv, ctx, dctx, lse2, B, T2, H, d, key_len, cs, drop_p=0.1, seed=1), 5, flush),
+          "delta + persistent backward + finalize (incl. inverse RoPE)")
+    # ---- CTC
+    Vp = (V + 7) // 8 * 8
+    logits = (torch.randn(B, T2, Vp, device=dev, generator=g)).to(torch.bfloat16)[:, :, :V]
+    tg, tl = batch["targets"], batch["target_lengths"]
+    entry("ctc_loss_fwd_bwd", "hbm", 2.0 * B * T2 * V * 2, _timed(lambda: L.ctc_loss_fwd_bwd(logits, tg, key_len, tl), 5, flush),
+          "rowstats + alpha/beta (serial lattice: B CTAs, T' dependent steps) + gradient")
+    return out
+
+
 # --------------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch.distributed as dist
     from turkish_asr_model_b200 import _lib as L
+    from turkish_asr_model_b200.data.preprocessing import SpecAugment, SpeedPerturbation
     from turkish_asr_model_b200.model import TurkishASRModel
     from turkish_asr_model_b200.trainer import Trainer
 
@@ -230,20 +411,37 @@ def run_gpu(args):
 
     class Cfg:
         log_interval = 10 ** 9
-    trainer = Trainer(model, None, opt, sched, dev, Cfg(), None, gradient_clip=1.0, accumulation_steps=1)
+    augment = args.workload == "augment"
+    K, W = args.steps, args.warmup
+    # K distinct bucketed batches (at most 24): each shape is captured once in an untimed pass, the W warm-up steps and
+    # the K timed steps then replay them
+    n_distinct = max(1, min(K, 24))
+    trainer = Trainer(model, None, opt, sched, dev, Cfg(), None, gradient_clip=1.0, accumulation_steps=1,
+                      max_cached_graphs=2 * n_distinct + 2, max_graph_samples=SR * (24 if augment else 20))
     if args.no_graphs:
         trainer.use_cuda_graphs = False
-
-    K, W = args.steps, args.warmup
-    # every distinct batch shape is seen (and its CUDA graph captured) during warm-up
-    n_distinct = max(1, min(K + W, 12, W))
     batches = make_batches(n_distinct, rank, world)
+    spec, speedp = SpecAugment(), SpeedPerturbation(SPEEDS)
     dev_batches = []
-    for b in batches:
-        dev_batches.append({"waves": synth_waves(b, dev), "n_samples": b["n_samples"].to(dev), "targets": b["targets"].to(dev),
-                            "target_lengths": b["target_lengths"].to(dev), "tmax": 1 + int(b["n_samples"].max()) // 160,
-                            "audio_s": float(b["n_samples"].sum()) / SR,
-                            "padded_s": float(b["n_samples"].max()) * len(b["n_samples"]) / SR})
+    for bi, b in enumerate(batches):
+        db = {"waves": synth_waves(b, dev), "n_samples": b["n_samples"].to(dev), "targets": b["targets"].to(dev),
+              "target_lengths": b["target_lengths"].to(dev), "tmax": 1 + int(b["n_samples"].max()) // 160,
+              "n_cpu": b["n_samples"], "audio_s": float(b["n_samples"].sum()) / SR,
+              "padded_s": float(b["n_samples"].max()) * len(b["n_samples"]) / SR}
+        if augment:  # per-utterance draws as the reference's dataset makes them (data/preprocessing.py:211, :167-174)
+            gs = torch.Generator().manual_seed(b["seed"] + 5)
+            db["speeds"] = [SPEEDS[int(torch.randint(3, (1,), generator=gs))] for _ in range(CFG["batch"])]
+            new_len = [-(-m * int(n) // o) for n, (o, m) in zip(b["n_samples"].tolist(),
+                                                               [(1, 1) if s == 1.0 else speedp.freqs(s, SR) for s in db["speeds"]])]
+            frames = [1 + n // 160 for n in new_len]
+            state = torch.random.get_rng_state()
+            torch.manual_seed(b["seed"] + 6)
+            params = [spec.mask_params(f, 80) for f in frames]
+            torch.random.set_rng_state(state)
+            flat_p = [[(0 if a == "f" else 1), int(s), int(e)] for per in params for (a, s, e) in per]
+            db["spec"] = torch.tensor(flat_p, dtype=torch.int32).view(CFG["batch"], 4, 3).to(dev)
+            db["new_len"] = torch.tensor(new_len, dtype=torch.int64)
+        dev_batches.append(db)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -251,11 +449,19 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def resident_step(i):
-        b = dev_batches[i % n_distinct]
-        return trainer.train_step_waveforms(b["waves"], b["n_samples"], b["targets"], b["target_lengths"], tmax=b["tmax"])
+    def step_on(waves, n_cpu, db, tmax=None):
+        if augment:
+            y, new_len = speedp.apply_batch(waves, n_cpu, SR, speeds=db["speeds"])
+            return trainer.train_step_waveforms(y, new_len, db["targets"], db["target_lengths"], spec_params=db["spec"])
+        return trainer.train_step_waveforms(waves, db["n_samples"], db["targets"], db["target_lengths"], tmax=tmax)
 
-    # ---- warm-up + timed region (device-resident inputs)
+    def resident_step(i):
+        db = dev_batches[i % n_distinct]
+        return step_on(db["waves"], db["n_cpu"], db, tmax=db["tmax"])
+
+    # ---- untimed capture pass + warm-up + timed region (device-resident inputs)
+    for i in range(n_distinct):
+        resident_step(i)
     for i in range(W):
         resident_step(i)
     sync_all()
@@ -263,6 +469,7 @@ def run_gpu(args):
     if rank == 0:
         clocks.start()
     launches0 = L.lib().tasr_launch_count() + trainer.graph_kernel_launches
+    trainer.timing = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     audio = 0.0
     padded = 0.0  # audio seconds including the zero padding to the longest utterance of each batch (what is computed)
@@ -276,6 +483,16 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     launches = L.lib().tasr_launch_count() + trainer.graph_kernel_launches - launches0
     final_loss = float(loss.detach())
+    # per-rank breakdown of the data-parallel step: own compute (graph A + B), wait for the gradient exchange
+    # (all-reduce not hidden under graph B + waiting for slower ranks), optimizer
+    evs = trainer.timing.get("events", [])
+    trainer.timing = None
+    if world > 1 and evs and len(evs[0]) == 4:
+        compute = sum(e[0].elapsed_time(e[1]) for e in evs) / len(evs)
+        exposed = sum(e[1].elapsed_time(e[2]) for e in evs) / len(evs)
+        optim = sum(e[2].elapsed_time(e[3]) for e in evs) / len(evs)
+    else:
+        compute, exposed, optim = ms / K, 0.0, 0.0
 
     # ---- end-to-end: pinned host buffers -> H2D -> step -> D2H of the loss, every step
     host_batches = []
@@ -289,8 +506,12 @@ def run_gpu(args):
     seen = {"n": 0, "last": 0.0}
 
     def e2e_step(i):
-        hb = host_batches[i % n_distinct]
-        l = trainer.train_step_waveforms(hb["waves"], hb["n_samples"], hb["targets"], hb["target_lengths"])
+        hb, db = host_batches[i % n_distinct], dev_batches[i % n_distinct]
+        if augment:
+            l = step_on(hb["waves"].to(dev, non_blocking=True), hb["n_samples"],
+                        dict(db, targets=hb["targets"], target_lengths=hb["target_lengths"]))
+        else:
+            l = trainer.train_step_waveforms(hb["waves"], hb["n_samples"], hb["targets"], hb["target_lengths"])
         k = seen["n"] & 1
         loss_host[k].copy_(l.detach().reshape(1), non_blocking=True)
         loss_evt[k].record()
@@ -318,13 +539,28 @@ def run_gpu(args):
     # ---- max over ranks, sum of audio
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     a = torch.tensor([audio, audio_e2e, padded], dtype=torch.float64, device=dev)
+    per_rank = torch.tensor([ms / K, compute, exposed, optim, padded / K], dtype=torch.float64, device=dev)
+    gathered = [torch.zeros_like(per_rank) for _ in range(world)]
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(a, op=dist.ReduceOp.SUM)
+        dist.all_gather(gathered, per_rank)
+    else:
+        gathered = [per_rank]
     ms, ms_e2e = float(t[0]), float(t[1])
     audio, audio_e2e, padded = float(a[0]), float(a[1]), float(a[2])
+    dp_info = None
+    if world > 1:
+        rows = [[round(float(v), 4) for v in gr.tolist()] for gr in gathered]
+        dp_info = {"per_rank_ms_per_step": [r[0] for r in rows], "per_rank_compute_ms": [r[1] for r in rows],
+                   "per_rank_exchange_wait_ms": [r[2] for r in rows], "per_rank_optimizer_ms": [r[3] for r in rows],
+                   "per_rank_padded_audio_s_per_step": [r[4] for r in rows],
+                   "note": "compute = graph A (mel+fwd+CTC+block backward) + graph B (subsampler backward, the body all-reduce "
+                           "runs under it); exchange_wait = what the main stream still waits for before the optimizer "
+                           "(uncovered all-reduce time + waiting for slower ranks: ranks hold different slices of a length-sorted "
+                           "global bucket); the fastest rank's wait minus the slowest rank's wait is the straggler share"}
 
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM), CUDA events around each launch, rank 0
+    # ---- rooflines (rank 0): the tcgen05 GEMM family replayed back to back + one entry per other kernel family
     roofline = None
     cpu_baseline = None
     if rank == 0:
@@ -333,15 +569,22 @@ def run_gpu(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        except Exception:
+            pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         hbm_peak = float(peaks.get("hbm_gbs", 6550.0))
+        big = max(range(n_distinct), key=lambda i: dev_batches[i]["tmax"])
+        bigb = dev_batches[big]
         # All tcgen05 GEMM launches of one step are recorded (argument structs, operands kept alive) and then
         # replayed back to back as ONE CUDA graph between two CUDA events: device time of exactly those kernels,
         # no host launch gaps.
         trainer.use_cuda_graphs = False
         trainer.world_size = 1  # rank-local pass: no collectives (the other ranks are not in this branch)
         L.GEMM_PROFILE = []
-        resident_step(0)
+        trainer.train_step_waveforms(bigb["waves"], bigb["n_samples"], bigb["targets"], bigb["target_lengths"], tmax=bigb["tmax"])
         torch.cuda.synchronize()
         prof, L.GEMM_PROFILE = L.GEMM_PROFILE, None
         flops = sum(p[0] for p in prof)
@@ -376,45 +619,42 @@ def run_gpu(args):
         r1.record()
         torch.cuda.synchronize()
         gms = r0.elapsed_time(r1) / reps
-        step_ms_this_batch = None
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         trainer.use_cuda_graphs = not args.no_graphs
-        resident_step(0)
+        args_big = (bigb["waves"], bigb["n_samples"], bigb["targets"], bigb["target_lengths"])
+        trainer.train_step_waveforms(*args_big, tmax=bigb["tmax"])
         s0.record()
-        resident_step(0)
+        trainer.train_step_waveforms(*args_big, tmax=bigb["tmax"])
         s1.record()
         torch.cuda.synchronize()
         step_ms_this_batch = s0.elapsed_time(s1)
+        src_t = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
+        src_h = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6550 GB/s"
         tensor_view = {"achieved": flops / (gms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                       "frac": flops / (gms * 1e-3) / 1e12 / peak, "flops_per_step": flops,
-                       "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"}
+                       "frac": flops / (gms * 1e-3) / 1e12 / peak, "flops_per_step": flops, "peak_source": src_t}
         # the same launches against the HBM roof (most of them have K = 256: operands + outputs dominate)
         hbm_view = {"achieved": gbytes / (gms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": gbytes / (gms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_step": gbytes,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6550 GB/s"}
-        # the binding roof is the one the family is closer to (larger fraction = larger lower bound on its time)
-        bound = "hbm" if hbm_view["frac"] >= tensor_view["frac"] else "tensor"
-        prim = hbm_view if bound == "hbm" else tensor_view
-        roofline = {"bound": bound, "kernel": "gemm_tc_kernel (persistent tcgen05 bf16 GEMM; all %d fwd/dgrad/wgrad launches "
-                                              "of one step replayed back to back)" % len(prof),
-                    "achieved": prim["achieved"], "peak": prim["peak"], "unit": prim["unit"], "frac": prim["frac"],
-                    "traffic": None, "peak_source": prim["peak_source"],
+                    "frac": gbytes / (gms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_step": gbytes, "peak_source": src_h}
+        # dense contractions are measured against the tensor roof (primary); the HBM view explains the gap
+        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (persistent tcgen05 bf16 GEMM; all %d fwd/dgrad/wgrad launches "
+                                                 "of one step replayed back to back)" % len(prof),
+                    "achieved": tensor_view["achieved"], "peak": peak, "unit": "TFLOP/s", "frac": tensor_view["frac"],
+                    "traffic": traffic.get("gemm_family"), "peak_source": src_t,
                     "launches_per_step": len(prof), "gemm_ms_per_step": gms, "step_share": gms / step_ms_this_batch,
-                    "tensor_view": tensor_view, "hbm_view": hbm_view}
-        del prof
+                    "step_ms_this_batch": step_ms_this_batch, "tensor_view": tensor_view, "hbm_view": hbm_view}
+        del prof, gg
+        try:
+            roofline["kernels"] = kernel_rooflines(model, bigb, dev, peaks, traffic)
+        except Exception as e:  # never lose the headline line to a side measurement
+            roofline["kernels_error"] = repr(e)[:300]
         if world == 1 and not args.no_cpu:
-            threads = os.cpu_count() or 1
-            v, spp = time_cpu(2, 1, threads, batches)
-            cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                            "sample": "first 8 utterances of 2 bucketed batches (5-15 s), full train step in fp32 on the "
-                                      "oracle port of the reference (torch CPU; dropout not modelled, which favours the CPU arm), "
-                                      "%.1f s/step" % spp}
+            cpu_baseline = cpu_baseline_subprocess()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": audio / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": workload_config(world),
+            "data": "synthetic", "config": dict(workload_config(world, args.workload), distinct_batches=n_distinct),
             "e2e": {"value": audio_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // K,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
@@ -422,7 +662,82 @@ def run_gpu(args):
             # `value` counts real (unpadded) audio; the same run counted in padded seconds
             "padded_audio_seconds_per_second": padded / (ms * 1e-3),
         }
+        if dp_info is not None:
+            line["data_parallel"] = dp_info
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------- configs[3]
+def run_infer60(args):
+    """Long-form inference: 32 x 60 s per GPU through BatchedInference.transcribe_ids (log-mel, encoder with the
+    key-padding mask, argmax + collapse on the GPU).  Replicas only (no exchange step)."""
+    import torch.distributed as dist
+    from turkish_asr_model_b200 import _lib as L
+    from turkish_asr_model_b200.inference import BatchedInference
+    from turkish_asr_model_b200.model import TurkishASRModel
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = TurkishASRModel(CFG["n_mels"], CFG["d_model"], CFG["n_heads"], CFG["n_blocks"], CFG["vocab"], dropout=0.1).to(dev)
+    inf = BatchedInference(model)
+    B, N = 32, 60 * SR
+    K, W = args.steps, args.warmup
+    g = torch.Generator().manual_seed(1234 + rank)
+    ns = torch.full((B,), N, dtype=torch.int64)
+    ns[1::4] = N - 3 * SR  # ragged lengths exercise the padding mask
+    host = [(0.1 * torch.randn(B, N, generator=g)).pin_memory() for _ in range(2)]
+    devw = [h.to(dev) for h in host]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for i in range(W):
+        inf.transcribe_ids(devw[i & 1], ns)
+    sync_all()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = L.lib().tasr_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        out, lengths = inf.logits(devw[i & 1], ns)
+        L.argmax_collapse(out, lengths.to(dev))
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = L.lib().tasr_launch_count() - n0
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    d2h = 0
+    for i in range(K):
+        ids = inf.transcribe_ids(host[i & 1].to(dev, non_blocking=True), ns)  # token ids back on the host
+        d2h += sum(len(s) for s in ids) * 8
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1)
+    clock_info = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    audio = float(ns.sum()) / SR * K * world
+    if rank == 0:
+        print(json.dumps({
+            "metric": "inference_audio_seconds_per_second", "value": audio / (float(t[0]) * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": float(t[0]) / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world, "infer60"),
+            "e2e": {"value": audio / (float(t[1]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * N * 4,
+                    "d2h_bytes_per_step": d2h // K, "ms_per_step": float(t[1]) / K},
+            "gpu_launches": int(launches), "clocks": clock_info}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -438,6 +753,8 @@ def main():
                     help="eager launches instead of per-shape CUDA graphs (under DP: bucketed all-reduce overlapped with backward)")
     ap.add_argument("--model", default="default", choices=["default", "conformer-m"],
                     help="default = BASELINE configs[1] (the headline); conformer-m = configs[2] (d_model 512, 8 heads, 16 blocks)")
+    ap.add_argument("--workload", default="train", choices=["train", "augment", "infer60"],
+                    help="train = the headline; augment = configs[4]; infer60 = configs[3]")
     args = ap.parse_args()
     if args.model == "conformer-m":
         CFG.update(d_model=512, n_heads=8, n_blocks=16)
@@ -448,7 +765,10 @@ def main():
         args.warmup = 3
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
-    run_gpu(args)
+    if args.workload == "infer60":
+        run_infer60(args)
+    else:
+        run_gpu(args)
 
 
 if __name__ == "__main__":

@@ -46,6 +46,8 @@ uint64_t tasr_launch_count(void);
 /* Optional device-resident counter added to every dropout seed at kernel run time (NULL to disable), so that a
  * captured CUDA graph draws fresh dropout masks on every replay.  Process-global configuration. */
 int tasr_set_dropout_seed_ptr(const uint64_t* dev_ptr);
+/* The pointer set by the last tasr_set_dropout_seed_ptr call (the owner clears it before freeing the counter). */
+const uint64_t* tasr_get_dropout_seed_ptr(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contractions on tcgen05 / TMEM (bf16 in, fp32 accumulate), operands staged by TMA.
@@ -100,9 +102,6 @@ typedef struct tasr_gemm_args {
 } tasr_gemm_args;
 
 int tasr_gemm_bf16(const tasr_gemm_args* args, tasr_stream_t stream);
-/* Same contract, plain CUDA-core kernel.  Debug/triage aid for the tests only; never used by the
- * product path. */
-int tasr_gemm_bf16_debug(const tasr_gemm_args* args, tasr_stream_t stream);
 
 /* One-time initialisation of immutable per-device constant tables (FFT twiddles).  Synchronous;
  * call once per process and device before the first kernel call (the Python binding does). */
@@ -201,17 +200,10 @@ int tasr_mqa_attention_bwd(const void* qkv, const void* ctx, const void* dctx, c
                            void* dqkv, void* workspace, size_t workspace_bytes, tasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Conv2d subsampler pieces (conv2 itself = tasr_gemm_bf16 on the im2col operand, SiLU epilogue).
- * Replaces: model/conformer.py:150-155,177-183.
- *   conv1_im2col: x (B,T,F) fp32 -> col (B*T2*F2, 9*d) bf16, column (kh*3+kw)*d + c,
- *                 value silu(conv1(x))[b,c,2*t2-1+kh,2*f2-1+kw] (0 in the padding).
- *   col2im_conv1_bwd: dcol -> dW1 (d,1,3,3), db1 (d) accumulated (+=).
+ * Weight re-packing for the subsampler GEMMs.
+ * Replaces: the permute/view of model/conformer.py:183 (folded into the weight layout instead of the activations).
  *   pack_weight_remap: out_bf16[n][(k % q)*(K/q) + k/q] = in_f32[n][k]  (conv2: q=9; input_proj: q=F2)
  * ---------------------------------------------------------------------------------------------- */
-int tasr_conv1_im2col(const float* x, int B, int T, int F, int d, const float* w1, const float* b1, void* col,
-                      tasr_stream_t stream);
-int tasr_col2im_conv1_bwd(const void* dcol, const float* x, int B, int T, int F, int d, const float* w1,
-                          const float* b1, float* dw1, float* db1, tasr_stream_t stream);
 int tasr_pack_weight_remap(const float* in, int64_t N, int K, int q, void* out, tasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
-"""The reference arm of bench.py runs on the CPU (oracle port of the reference): check the JSON contract the driver
-reads (one line, the tier's keys) without a GPU."""
+"""The reference arm of bench.py runs on the CPU (the unmodified reference staged under baseline/_ref by
+oracle/install_ref.py, or the oracle port when it is not staged): check the JSON contract the driver reads (one line,
+the tier's keys) without a GPU."""
 import json
 import os
 import subprocess
@@ -16,7 +17,8 @@ def test_reference_arm_json_line():
     assert line["metric"] == "train_audio_seconds_per_second" and line["unit"] == "audio-s/s"
     assert line["higher_is_better"] is True and line["scaling"] == "weak" and line["vs_baseline"] is None
     assert line["value"] > 0 and line["n_gpus"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    staged = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "trainer", "trainer.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]

@@ -17,17 +17,16 @@ def _ref(A, B, a_mn, b_mn):
     return a @ b.t()
 
 
-@pytest.mark.parametrize("debug", [False, True])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 256), (304, 200, 136), (2008, 1000, 256)])
-def test_gemm_store(cuda, M, N, K, a_mn, b_mn, debug):
+def test_gemm_store(cuda, M, N, K, a_mn, b_mn):
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K + a_mn * 2 + b_mn)
     A = torch.randn((K, M) if a_mn else (M, K), generator=g).to(torch.bfloat16).to(cuda)
     B = torch.randn((K, N) if b_mn else (N, K), generator=g).to(torch.bfloat16).to(cuda)
     bias = torch.randn(N, generator=g).to(cuda)
     out = torch.full((M, N), float("nan"), device=cuda, dtype=torch.float32)
     L.gemm(M, N, K, A, A.stride(0), B, B.stride(0), L.EPI_STORE, out, N, a_mn=a_mn, b_mn=b_mn, out_f32=1,
-           bias=bias, debug=debug)
+           bias=bias)
     torch.cuda.synchronize()
     ref = _ref(A, B, a_mn, b_mn) + bias.double().cpu()
     err = (out.double().cpu() - ref).abs().max().item()

@@ -227,31 +227,6 @@ def test_mqa_attention_dropout_mask_consistent(cuda):
 
 
 # ------------------------------------------------------------------ subsampler
-@pytest.mark.parametrize("B,T,d", [(2, 203, 256), (1, 64, 512), (3, 9, 256)])
-def test_conv1_im2col_and_bwd(cuda, B, T, d):
-    Fm = 80
-    g = torch.Generator().manual_seed(T)
-    x = torch.randn(B, T, Fm, generator=g)
-    w1 = torch.randn(d, 1, 3, 3, generator=g) / 3
-    b1 = torch.randn(d, generator=g) / 3
-    T1, F1, T2, F2 = L.sub_dims(T, Fm)
-    w1d, b1d = w1.double().requires_grad_(True), b1.double().requires_grad_(True)
-    y1 = F.silu(F.conv2d(x.double().unsqueeze(1), w1d, b1d, stride=2, padding=1))  # (B,d,T1,F1)
-    assert y1.shape[2:] == (T1, F1)
-    cols = F.unfold(y1, kernel_size=3, padding=1, stride=2)  # (B, d*9, T2*F2), row index c*9 + kh*3 + kw
-    cols = cols.view(B, d, 9, T2 * F2).permute(0, 3, 2, 1).reshape(B * T2 * F2, 9 * d)
-    col = L.conv1_im2col(x.to(cuda), w1.to(cuda), b1.to(cuda))
-    torch.cuda.synchronize()
-    assert col.shape == cols.shape
-    assert rel_err(col, cols.detach()) < 6e-3
-    dcol = bf(torch.randn(cols.shape, generator=g))
-    cols.backward(dcol.double())
-    dw1, db1 = torch.zeros(d, 1, 3, 3, device=cuda), torch.zeros(d, device=cuda)
-    L.col2im_conv1_bwd(dcol.to(cuda), x.to(cuda), w1.to(cuda), b1.to(cuda), dw1, db1)
-    torch.cuda.synchronize()
-    assert rel_err(dw1, w1d.grad) < 1e-3 and rel_err(db1, b1d.grad) < 1e-3
-
-
 @pytest.mark.parametrize("B,T,d", [(2, 203, 256), (1, 130, 512), (3, 9, 256), (2, 64, 128)])
 def test_implicit_conv_subsampler(cuda, B, T, d):
     """conv1_fwd + conv2_fwd / dgrad / wgrad + conv1_bwd (implicit GEMM) vs F.conv2d autograd in float64."""

@@ -14,9 +14,10 @@ from oracle import ctc as octc
 from oracle import mel as om
 from oracle import sampler as osamp
 
+from golden_inputs import GCFG, big_case_inputs, trainer_golden_batches
+
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 REF = "/root/reference"
-GCFG = dict(n_mels=80, d_model=128, n_heads=2, n_blocks=1, n_classes=32)
 
 
 def _golden_model_sd():
@@ -142,3 +143,53 @@ def test_ctc_oracle_vs_torch_ctc_loss():
     assert abs(float(loss) - float(ref.detach())) < 1e-9
     assert np.abs(grad - logits.grad.numpy()).max() < 1e-9
     assert np.abs(grad[3]).max() == 0.0 and np.abs(grad[1, 25:]).max() == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# full-depth fixtures (BASELINE configs[0]/[1] depth: 8 blocks d=256 V=1000 B=8x10 s; configs[2]: 16 blocks d=512)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_golden.npz", "cm_golden.npz"])
+def test_full_depth_oracle_vs_golden(name):
+    g = np.load(os.path.join(GOLD, name))
+    m, x, il, targets, tl, (d, H, nb, V, ts, vs) = big_case_inputs(g)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    pnames = [n for n, _ in m.named_parameters()]
+    sdr = {k: (v.clone().requires_grad_(True) if k in pnames else v) for k, v in sd.items()}
+    logits = oc.forward(x, il, sdr, H, nb, training=True)
+    ref = g["logits_sub"]
+    assert np.abs(logits.detach()[:, ::ts, ::vs].numpy() - ref).max() < 1e-4 * float(g["logits_absmax"])
+    loss = oc.ctc_loss_torch(logits, targets, il, tl)
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    loss.backward()
+    for pname, ref_norm in zip(g["grad_names"], g["grad_norms"]):
+        gr = sdr[str(pname)].grad
+        if ref_norm < 0:
+            assert gr is None, pname
+        else:
+            assert abs(float(gr.norm()) - ref_norm) <= 2e-3 * max(ref_norm, 1e-6) + 1e-6, pname
+
+
+@pytest.mark.parametrize("accum", [1, 2])
+def test_trainer_oracle_vs_golden(accum):
+    """oracle/trainer.py against the reference's own Trainer.train_epoch (3 batches, CPU): average loss, step
+    counters, scheduler position and the parameter update itself (every 16th element of every parameter)."""
+    from oracle.trainer import TrainerOracle
+    g = np.load(os.path.join(GOLD, "trainer_golden.npz"))
+    m, sd = _golden_model_sd()
+    pnames = [n for n, _ in m.named_parameters()]
+    tr = TrainerOracle(sd, pnames, GCFG["n_heads"], GCFG["n_blocks"], accumulation_steps=accum,
+                       scheduler_fn=lambda o: torch.optim.lr_scheduler.OneCycleLR(o, max_lr=5e-4, total_steps=100,
+                                                                                  pct_start=0.1, anneal_strategy="cos"))
+    init = torch.cat([sd[n].reshape(-1) for n in pnames]).clone()
+    avg, _ = tr.train_epoch(trainer_golden_batches())
+    assert abs(avg - float(g["avg_loss_accum%d" % accum])) < 1e-5 * abs(avg)
+    assert tr.global_step == int(g["global_step_accum%d" % accum])
+    assert tr.sched.last_epoch == int(g["sched_last_epoch_accum%d" % accum])
+    final = torch.cat([tr.sd[n].detach().reshape(-1) for n in pnames])
+    delta = (final - init)[::16].numpy()
+    ref = g["delta_sub_accum%d" % accum]
+    # AdamW's first steps move every weight by ~lr * sign(g): entries whose gradient is ~0 may flip, the rest agree
+    close = np.abs(delta - ref) <= 2e-5 + 1e-2 * np.abs(ref)
+    assert close.mean() > 0.995, close.mean()
+    cos = float((delta * ref).sum() / (np.linalg.norm(delta) * np.linalg.norm(ref)))
+    assert cos > 0.999, cos

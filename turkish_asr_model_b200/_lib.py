@@ -22,8 +22,8 @@ _SIGNATURES = {
     "tasr_init": (I, []),
     "tasr_launch_count": (U64, []),
     "tasr_set_dropout_seed_ptr": (I, [P]),
+    "tasr_get_dropout_seed_ptr": (P, []),
     "tasr_gemm_bf16": (I, [P, P]),
-    "tasr_gemm_bf16_debug": (I, [P, P]),
     "tasr_mel_filter_ranges": (I, [P, I, P, P]),
     "tasr_mel_workspace_bytes": (Z, [I, I]),
     "tasr_mel_forward": (I, [P, L, P, I, I, P, P, P, I, I, I, I, P, P, Z, P]),
@@ -43,8 +43,6 @@ _SIGNATURES = {
     "tasr_mqa_attention_fwd": (I, [P, I, I, I, I, P, F, U64, P, P, P]),
     "tasr_mqa_attention_bwd_workspace_bytes": (Z, [I, I, I, I]),
     "tasr_mqa_attention_bwd": (I, [P, P, P, P, I, I, I, I, P, F, U64, P, P, P, Z, P]),
-    "tasr_conv1_im2col": (I, [P, I, I, I, I, P, P, P, P]),
-    "tasr_col2im_conv1_bwd": (I, [P, P, I, I, I, I, P, P, P, P, P]),
     "tasr_pack_weight_remap": (I, [P, L, I, I, P, P]),
     "tasr_conv1_fwd": (I, [P, I, I, I, I, P, P, P, P]),
     "tasr_conv1_bwd": (I, [P, P, I, I, I, I, P, P, P, P, P]),
@@ -102,16 +100,24 @@ def ptr(t):
 
 
 _ws_cache = {}
+_ws_retired = []  # replaced scratch buffers: captured CUDA graphs may still hold their addresses
 
 
 def workspace(nbytes, device):
-    """Reusable scratch buffer (per device); kernels of one stream run in order so sharing is safe."""
+    """Reusable scratch buffer (per device); kernels of one stream run in order so sharing is safe.
+    A buffer that has to grow is replaced by one of at least twice the size; the old one is kept allocated for the
+    life of the process because CUDA graphs captured earlier have its raw address baked in (geometric growth bounds
+    the retained memory by the size of the live buffer)."""
     key = (device.index if device.index is not None else torch.cuda.current_device())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():
             raise TasrError("scratch workspace would have to grow during CUDA-graph capture; run one eager step first")
-        buf = torch.empty(max(int(nbytes), 128 << 20), dtype=torch.uint8, device=device)
+        size = max(int(nbytes), 128 << 20)
+        if buf is not None:
+            size = max(size, 2 * buf.numel())
+            _ws_retired.append(buf)
+        buf = torch.empty(size, dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
 
@@ -151,7 +157,7 @@ class GemmArgs(C.Structure):
 
 def gemm(M, N, K, A, lda, B, ldb, epilogue, out, ldo, a_mn=0, b_mn=0, out_f32=0, out2=None, ldo2=0,
          bias=None, aux=None, ldaux=0, alpha=1.0, n_half=0, drop_p=0.0, seed=0, split_k=1,
-         remap_p0=0, remap_p1=0, debug=False):
+         remap_p0=0, remap_p1=0):
     require_cuda(A, B, out)
     a = GemmArgs()
     a.M, a.N, a.K = M, N, K
@@ -164,7 +170,7 @@ def gemm(M, N, K, A, lda, B, ldb, epilogue, out, ldo, a_mn=0, b_mn=0, out_f32=0,
     a.aux, a.ldaux = (aux.data_ptr() if aux is not None else 0), ldaux
     a.alpha, a.n_half, a.drop_p, a.seed = alpha, n_half, drop_p, seed
     a.split_k, a.remap_p0, a.remap_p1 = split_k, remap_p0, remap_p1
-    fn = lib().tasr_gemm_bf16_debug if debug else lib().tasr_gemm_bf16
+    fn = lib().tasr_gemm_bf16
     if GEMM_PROFILE is not None:  # bench.py roofline pass: remember every tcgen05 GEMM launch of a step
         nb = 2 if epilogue in (EPI_SWIGLU, EPI_GLU) else 1
         GEMM_PROFILE.append((2.0 * M * N * nb * K, a, (A, B, out, out2, bias, aux), (M, N * nb, K, epilogue, a_mn, b_mn)))
@@ -336,22 +342,6 @@ def mqa_bwd(qkv, ctx, dctx, lse2, B, T, H, d, key_lengths, cos_sin, drop_p=0.0, 
 def sub_dims(T, F):
     T1, F1 = (T - 1) // 2 + 1, (F - 1) // 2 + 1
     return T1, F1, (T1 - 1) // 2 + 1, (F1 - 1) // 2 + 1
-
-
-def conv1_im2col(x, w1, b1):
-    require_cuda(x, w1, b1)
-    B, T, F = x.shape
-    d = w1.shape[0]
-    _, _, T2, F2 = sub_dims(T, F)
-    col = torch.empty(B * T2 * F2, 9 * d, dtype=torch.bfloat16, device=x.device)
-    check(lib().tasr_conv1_im2col(ptr(x), B, T, F, d, ptr(w1), ptr(b1), ptr(col), stream_ptr()))
-    return col
-
-
-def col2im_conv1_bwd(dcol, x, w1, b1, dw1, db1):
-    B, T, F = x.shape
-    d = w1.shape[0]
-    check(lib().tasr_col2im_conv1_bwd(ptr(dcol), ptr(x), B, T, F, d, ptr(w1), ptr(b1), ptr(dw1), ptr(db1), stream_ptr()))
 
 
 def pack_weight_remap(w2d, q):

@@ -16,8 +16,12 @@ LIB = os.path.join(HERE, "libtasr_kernels.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
 ]
+# --use_fast_math (approximate division / sqrt / transcendentals, flush-to-zero) is an opt-in per translation unit:
+# the fp32 parity kernels (log-mel 1e-4 abs, CTC 1e-3 rel, AdamW) and the integer / index kernels compile with IEEE
+# arithmetic; the bf16-operand kernels, whose outputs are rounded to 8 bits of mantissa anyway, keep it.
+FAST_MATH = {"attention.cu", "conv1_tc.cu", "conv_gemm.cu", "dwconv.cu", "elementwise.cu", "gemm.cu", "norm.cu"}
 
 
 def _sources():
@@ -36,7 +40,7 @@ def _compile(src, force, hdr_mtime):
     if (not force and os.path.exists(obj) and os.path.getmtime(obj) >= os.path.getmtime(spath)
             and os.path.getmtime(obj) >= hdr_mtime):
         return obj, ""
-    cmd = [NVCC] + FLAGS + ["-c", spath, "-o", obj]
+    cmd = [NVCC] + FLAGS + (["--use_fast_math"] if src in FAST_MATH else []) + ["-c", spath, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

@@ -631,11 +631,11 @@ extern "C" int tasr_mqa_attention_fwd(const void* qkv, int B, int T, int H, int 
   p.ctx = reinterpret_cast<bf16*>(ctx);
   p.lse2 = lse2;
   constexpr int SMEM = 81920 + 64 + 1024 + 1024;  // tiles, barriers, row exchange, alignment slack
-  static bool attr_done = false;
-  if (!attr_done) {
+  static TasrPerDevice attr_done;
+  if (!attr_done.get()) {
     cudaError_t e = cudaFuncSetAttribute(mqa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return tasr_set_cuda_error(e);
-    attr_done = true;
+    attr_done.set();
   }
   dim3 grid(cdiv(T, BQ), H, B);
   mqa_fwd_kernel<<<grid, ATT_THREADS, SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
@@ -678,16 +678,12 @@ extern "C" int tasr_mqa_attention_bwd(const void* qkv, const void* ctx, const vo
   p.dqkv = reinterpret_cast<bf16*>(dqkv);
   constexpr int SMEM_MAX = 163840 + 64 + (ATT_BWD_MAX_B + 1) * 4 + 1024;
   const int smem_bytes = 163840 + 64 + (B + 1) * 4 + 1024;
-  static bool attr_done = false;
-  static int n_sms = 148;
-  if (!attr_done) {
+  static TasrPerDevice attr_done;
+  const int n_sms = tasr_num_sms();
+  if (!attr_done.get()) {
     e = cudaFuncSetAttribute(mqa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e != cudaSuccess) return tasr_set_cuda_error(e);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sms <= 0) n_sms = 148;
-    attr_done = true;
+    attr_done.set();
   }
   const long long max_units = (long long)B * cdiv(T, BKV) * H * cdiv(T, BQ);
   const int grid = (int)imin64(n_sms, max_units);

@@ -63,6 +63,35 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
 #endif
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// One-time-per-DEVICE flag (cudaFuncSetAttribute and friends are per device, a process may drive several GPUs).
+struct TasrPerDevice {
+  unsigned long long mask = 0ull;  // bit = device ordinal (ordinals >= 64 are simply redone on every call)
+  static int current() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+  }
+  bool get() const {
+    const int dev = current();
+    return dev < 64 && ((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> dev) & 1ull);
+  }
+  void set() {
+    const int dev = current();
+    if (dev < 64) __atomic_fetch_or(&mask, 1ull << dev, __ATOMIC_RELEASE);
+  }
+};
+// SM count of the current device (cached per device)
+static inline int tasr_num_sms() {
+  static int cache[64] = {0};
+  const int dev = TasrPerDevice::current();
+  if (dev < 64 && cache[dev] > 0) return cache[dev];
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev < 64) cache[dev] = n;
+  return n;
+}
 static inline long long imin64(long long a, long long b) { return a < b ? a : b; }
 
 // ----------------------------------------------------------------------------------------------

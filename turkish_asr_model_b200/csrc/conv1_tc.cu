@@ -417,11 +417,11 @@ int tasr_conv1_tc_fwd(const float* x, int B, int T, int F, int d, const float* w
   CUtensorMap tmY;
   if (make_out_map(&tmY, y1, p.npix) != TASR_OK) return TASR_ERR_CUDA;
   constexpr int SMEM = W_BYTES + 2 * P_BYTES + 2 * DZ_BYTES + 64 + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static TasrPerDevice attr_done;
+  if (!attr_done.get()) {
     cudaError_t e = cudaFuncSetAttribute(conv1_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return tasr_set_cuda_error(e);
-    attr_done = true;
+    attr_done.set();
   }
   const int grid = p.ntiles < tc_num_sms() ? p.ntiles : tc_num_sms();
   conv1_tc_fwd_kernel<<<grid, TC_THREADS, SMEM, st>>>(tmY, p);
@@ -441,11 +441,11 @@ int tasr_conv1_tc_bwd(const void* dy1, const float* x, int B, int T, int F, int 
   if (make_out_map(&tmG, const_cast<void*>(dy1), p.npix) != TASR_OK) return TASR_ERR_CUDA;
   constexpr int SMEM = W_BYTES + 2 * P_BYTES + 2 * DZ_BYTES + 64 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static TasrPerDevice attr_done;
+  if (!attr_done.get()) {
     cudaError_t e = cudaFuncSetAttribute(conv1_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return tasr_set_cuda_error(e);
-    attr_done = true;
+    attr_done.set();
   }
   const int grid = p.ntiles < tc_num_sms() ? p.ntiles : tc_num_sms();
   conv1_tc_bwd_kernel<<<grid, TC_THREADS, SMEM, st>>>(tmG, p);

@@ -657,11 +657,11 @@ int launch_conv(const CUtensorMap* cm, const CUtensorMap& tmW, const CUtensorMap
   static const bool mc_enabled = [] { const char* e = getenv("TASR_CONV_MC"); return !(e && e[0] == '0'); }();
   if (MODE != CONV_WGRAD && BN == 256 && p.tiles_n == 1 && p.splits == 1 && total >= 2 && g_sms >= 2 && mc_enabled) {
     auto kern = conv_gemm_kernel<MODE, BN, (MODE != CONV_WGRAD && BN == 256)>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static TasrPerDevice attr_done;
+    if (!attr_done.get()) {
       cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
       if (err != cudaSuccess) return tasr_set_cuda_error(err);
-      attr_done = true;
+      attr_done.set();
     }
     const long long pairs = (total + 1) / 2;
     const int grid = 2 * (int)(pairs < g_sms / 2 ? pairs : g_sms / 2);
@@ -669,11 +669,11 @@ int launch_conv(const CUtensorMap* cm, const CUtensorMap& tmW, const CUtensorMap
                               tmY, p);
   } else {
     auto kern = conv_gemm_kernel<MODE, BN, false>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static TasrPerDevice attr_done;
+    if (!attr_done.get()) {
       cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
       if (err != cudaSuccess) return tasr_set_cuda_error(err);
-      attr_done = true;
+      attr_done.set();
     }
     const int grid = (int)(total < g_sms ? total : g_sms);
     lerr = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)SMEM, st, cm[0], cm[1], cm[2], cm[3], tmW, tmZ, tmY, p);
@@ -711,11 +711,11 @@ extern "C" int tasr_conv1_fwd(const float* x, int B, int T, int F, int d, const 
   int grid = (int)imin64(cdiv(total, NWARP), 2 * g_sms);
   if (grid * NWARP < slices) grid = cdiv(slices, NWARP);
   const size_t smem = ((size_t)10 * dpad + NWARP * 2 * PSLOT * 2) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static TasrPerDevice attr_done;
+  if (!attr_done.get()) {
     cudaError_t e = cudaFuncSetAttribute(conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return tasr_set_cuda_error(e);
-    attr_done = true;
+    attr_done.set();
   }
   conv1_fwd_kernel<<<grid, NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, B, T, F, d, dpad, w1, b1, g.T1, g.F1,
                                                                               reinterpret_cast<bf16*>(y1));
@@ -738,11 +738,11 @@ extern "C" int tasr_conv1_bwd(const void* dy1, const float* x, int B, int T, int
   int grid = (int)imin64(cdiv(total, NWARP), 2 * g_sms);
   if (grid * NWARP < slices) grid = cdiv(slices, NWARP);
   const size_t smem = ((size_t)20 * dpad + NWARP * 2 * PSLOT * 2) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static TasrPerDevice attr_done;
+  if (!attr_done.get()) {
     cudaError_t e = cudaFuncSetAttribute(conv1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return tasr_set_cuda_error(e);
-    attr_done = true;
+    attr_done.set();
   }
   conv1_bwd_kernel<<<grid, NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(dy1), x, B, T, F, d,
                                                                               dpad, w1, b1, g.T1, g.F1, dw1, db1);

@@ -150,7 +150,8 @@ __global__ void ctc_alpha_beta_kernel(int T, int Smax, const long long* __restri
       const float aL1 = NS >= 2 ? cur[2 + NS - 2] : NEG_INF;
       float nll = -lse2(aL, aL1);
       nll_out[b] = nll;
-      if (nll != INFINITY && nll == nll) atomicAdd(loss, nll / (float)max(S, 1) / (float)B);
+      // zero_infinity zeroes infeasible (+inf) samples only: a NaN sample makes the mean NaN, like nn.CTCLoss
+      if (nll != INFINITY) atomicAdd(loss, nll / (float)max(S, 1) / (float)B);
     }
   } else if (threadIdx.x == 0) {
     nll_out[b] = (S == 0) ? 0.f : INFINITY;
@@ -184,7 +185,10 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const TL* __restrict__ lo
   const float nll = nll_in[b];
   TL* drow = dlogits + ((long long)b * T + t) * ld;
   if (t >= L || nll == INFINITY || nll != nll) {
-    for (int c = lane; c < V; c += 32) store_grad<TL, TL>(drow, c, 0.f);
+    // padding frames and infeasible samples: exactly 0 (zero_infinity); a NaN sample poisons its rows so that the
+    // non-finite gradient norm makes the optimizer skip the step (reference trainer/trainer.py:178-181)
+    const float fill = (nll != nll && t < L) ? nll : 0.f;
+    for (int c = lane; c < V; c += 32) store_grad<TL, TL>(drow, c, fill);
     return;
   }
   float* gam = sh_gam + wib * (Smax + 1);

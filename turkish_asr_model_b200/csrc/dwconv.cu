@@ -302,11 +302,11 @@ extern "C" int tasr_dwconv31_bwd(const void* dw, const void* u, const void* ab, 
   const int tiles_per_cta = cdiv(ntiles, nseg);
   dim3 grid_b(d / CC, cdiv(ntiles, tiles_per_cta), B);
   constexpr int WSMEM = ((ROWS + 1) + TT) * (CC / 2) * (int)sizeof(float2);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static TasrPerDevice attr_done;
+  if (!attr_done.get()) {
     cudaError_t e = cudaFuncSetAttribute(dwconv_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM);
     if (e != cudaSuccess) return tasr_set_cuda_error(e);
-    attr_done = true;
+    attr_done.set();
   }
   {
     int cz = 8;

@@ -108,6 +108,18 @@ __global__ void __launch_bounds__(NT) rope_kernel(bf16* __restrict__ qkv, long l
   }
 }
 
+// out[n][(k % q) * (K / q) + k / q] = bf16(in[n][k])      (conv2: q = 9, input_proj: q = F2)
+__global__ void __launch_bounds__(NT) pack_weight_remap_kernel(const float* __restrict__ in, long long N, int K, int q,
+                                                               bf16* __restrict__ out) {
+  const int inner = K / q;
+  const long long total = N * K;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    const long long n = i / K;
+    const int k = (int)(i - n * K);
+    out[n * K + (long long)(k % q) * inner + k / q] = __float2bfloat16(in[i]);
+  }
+}
+
 }  // namespace
 
 extern "C" int tasr_cast_f32_bf16(const float* in, void* out, int64_t n, float alpha, float drop_p, uint64_t seed,
@@ -145,6 +157,14 @@ extern "C" int tasr_rope_inplace(void* qkv, int64_t M, int T, int ld, int rot_co
   const int grid = (int)imin64((long long)148 * 8, (total + NT - 1) / NT);
   rope_kernel<<<grid, NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<bf16*>(qkv), M, T, ld, rot_cols,
                                                                        cos_sin, inverse ? -1.f : 1.f);
+  TASR_CHECK_LAUNCH();
+  return TASR_OK;
+}
+
+extern "C" int tasr_pack_weight_remap(const float* in, int64_t N, int K, int q, void* out, tasr_stream_t stream) {
+  if (N <= 0 || K <= 0 || q <= 0 || K % q) return TASR_ERR_SHAPE;
+  const int grid = (int)imin64((long long)148 * 8, (N * K + NT - 1) / NT);
+  pack_weight_remap_kernel<<<grid, NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, N, K, q, reinterpret_cast<bf16*>(out));
   TASR_CHECK_LAUNCH();
   return TASR_OK;
 }

@@ -315,81 +315,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Debug CUDA-core kernel (tests / triage only): one thread per (row, 32-col chunk), direct stores
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dbg_store(void* base, long long ld, int is_f32, long long r, int c, float v) {
-  if (is_f32) reinterpret_cast<float*>(base)[r * ld + c] = v;
-  else reinterpret_cast<bf16*>(base)[r * ld + c] = __float2bfloat16(v);
-}
-__global__ void gemm_debug_kernel(const bf16* A, long long lda, int a_mn, const bf16* B, long long ldb, int b_mn,
-                                  GemmDev p, int dual) {
-  const int chunks = (p.N + 15) / 16;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)p.M * chunks) return;
-  const int row = (int)(gid / chunks);
-  const int col0 = (int)(gid % chunks) * 16;
-  float lo[16], hi[16], t3[16];
-  for (int i = 0; i < 16; ++i) {
-    float s0 = 0.f, s1 = 0.f;
-    const int n = col0 + i;
-    if (n < p.N) {
-      for (int k = 0; k < p.K; ++k) {
-        float a = __bfloat162float(a_mn ? A[(long long)k * lda + row] : A[(long long)row * lda + k]);
-        float b = __bfloat162float(b_mn ? B[(long long)k * ldb + n] : B[(long long)n * ldb + k]);
-        s0 += a * b;
-        if (dual) {
-          float b1 = __bfloat162float(b_mn ? B[(long long)k * ldb + p.n_half + n] : B[(long long)(p.n_half + n) * ldb + k]);
-          s1 += a * b1;
-        }
-      }
-    }
-    lo[i] = s0;
-    hi[i] = s1;
-  }
-  switch (p.epi) {
-    case TASR_EPI_STORE: epilogue_math<TASR_EPI_STORE, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
-    case TASR_EPI_RESID: epilogue_math<TASR_EPI_RESID, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
-    case TASR_EPI_SWIGLU: epilogue_math<TASR_EPI_SWIGLU, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
-    case TASR_EPI_GLU: epilogue_math<TASR_EPI_GLU, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
-    case TASR_EPI_SILU: epilogue_math<TASR_EPI_SILU, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
-    case TASR_EPI_SWIGLU_BWD: epilogue_math<TASR_EPI_SWIGLU_BWD, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
-    case TASR_EPI_GLU_BWD: epilogue_math<TASR_EPI_GLU_BWD, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
-    case TASR_EPI_SILU_BWD: epilogue_math<TASR_EPI_SILU_BWD, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
-    default: epilogue_math<TASR_EPI_ATOMIC, 16>(p, gemm_drop_seed32(p), row, col0, lo, hi, t3); break;
-  }
-  const bool f32_out = (p.epi == TASR_EPI_RESID) || (p.epi == TASR_EPI_ATOMIC) || (p.epi == TASR_EPI_STORE && p.out_f32);
-  for (int i = 0; i < 16; ++i) {
-    const int c = col0 + i;
-    if (c >= p.N) break;
-    switch (p.epi) {
-      case TASR_EPI_SWIGLU:
-      case TASR_EPI_GLU:
-        dbg_store(p.out, p.ldo, 0, row, c, t3[i]);
-        dbg_store(p.out2, p.ldo2, 0, row, c, lo[i]);
-        dbg_store(p.out2, p.ldo2, 0, row, p.n_half + c, hi[i]);
-        break;
-      case TASR_EPI_SILU:
-        dbg_store(p.out, p.ldo, 0, row, c, t3[i]);
-        if (p.out2) dbg_store(p.out2, p.ldo2, 0, row, c, lo[i]);
-        break;
-      case TASR_EPI_SWIGLU_BWD:
-      case TASR_EPI_GLU_BWD:
-        dbg_store(p.out, p.ldo, 0, row, c, lo[i]);
-        dbg_store(p.out, p.ldo, 0, row, p.n_half + c, hi[i]);
-        break;
-      case TASR_EPI_ATOMIC: {
-        int cc = c;
-        if (p.remap_p0 > 0) cc = (c % p.remap_p0) * p.remap_p1 + c / p.remap_p0;
-        atomicAdd(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + cc, lo[i]);
-      } break;
-      default:
-        dbg_store(p.out, p.ldo, f32_out ? 1 : 0, row, c, lo[i]);
-        break;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -397,7 +322,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled g_encode = nullptr;
 std::once_flag g_encode_once;
-int g_num_sms = 0;
 
 void init_encode() {
   void* fn = nullptr;
@@ -405,10 +329,6 @@ void init_encode() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
       qres == cudaDriverEntryPointSuccess)
     g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  if (g_num_sms <= 0) g_num_sms = 148;
 }
 
 int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, uint64_t inner, uint64_t outer,
@@ -508,18 +428,19 @@ int launch_tc(const tasr_gemm_args* a, GemmDev& p, cudaStream_t st) {
     tmO2 = tmO;
   }
   auto kern = gemm_tc_kernel<EPI, BN, STAGES, RINGG, A_MN, B_MN>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static TasrPerDevice attr_done;
+  if (!attr_done.get()) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (err != cudaSuccess) return tasr_set_cuda_error(err);
-    attr_done = true;
+    attr_done.set();
   }
   p.tiles_m = cdiv(a->M, BM);
   p.tiles_n = cdiv(a->N, TILE_N);
   const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
   // as few CTAs as finish in the same number of rounds: e.g. 332 tiles -> 3 rounds -> 111 CTAs with 3 tiles each instead
   // of 148 with 2-3; the makespan is the same and the other SMs stay free for the kernels of the second stream
-  const long long rounds = (total + g_num_sms - 1) / g_num_sms;
+  const int num_sms = tasr_num_sms();
+  const long long rounds = (total + num_sms - 1) / num_sms;
   const int grid = (int)((total + rounds - 1) / rounds);
   cudaError_t lerr = launch_pdl(kern, dim3(grid), dim3(G_THREADS), (size_t)SMEM, st, tmA, tmB, tmO, tmO2, p);
   if (lerr != cudaSuccess) return tasr_set_cuda_error(lerr);
@@ -534,7 +455,7 @@ inline bool use_wide(int M, int N, int splits) {
   if (!((N % 256 == 0) || (N > 512 && (N % 256) > 128))) return false;
   const long long tm = (M + BM - 1) / BM;
   const long long wide_tiles = tm * ((N + 255) / 256) * splits, narrow_tiles = tm * ((N + 127) / 128) * splits;
-  const long long sms = g_num_sms > 0 ? g_num_sms : 148;
+  const long long sms = tasr_num_sms();
   const long long cost_wide = ((wide_tiles + sms - 1) / sms) * 256, cost_narrow = ((narrow_tiles + sms - 1) / sms) * 128;
   return cost_wide <= cost_narrow;
 }
@@ -600,20 +521,4 @@ extern "C" int tasr_gemm_bf16(const tasr_gemm_args* a, tasr_stream_t stream) {
     default: break;
   }
   return TASR_ERR_SHAPE;  // epilogue / operand-major combination not instantiated (see include/tasr_kernels.h)
-}
-
-extern "C" int tasr_gemm_bf16_debug(const tasr_gemm_args* a, tasr_stream_t stream) {
-  GemmDev p;
-  bool dual;
-  int rc = fill_dev(a, &p, &dual);
-  if (rc) return rc;
-  p.kb_per_split = (a->K + BK - 1) / BK;
-  p.splits = 1;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long total = (long long)a->M * ((a->N + 15) / 16);
-  gemm_debug_kernel<<<cdiv(total, 128), 128, 0, st>>>(reinterpret_cast<const bf16*>(a->A), a->lda, a->a_mn_major,
-                                                      reinterpret_cast<const bf16*>(a->B), a->ldb, a->b_mn_major, p,
-                                                      dual ? 1 : 0);
-  TASR_CHECK_LAUNCH();
-  return TASR_OK;
 }

@@ -12,6 +12,10 @@ extern "C" int tasr_set_dropout_seed_ptr(const uint64_t* dev_ptr) {
   return TASR_OK;
 }
 
+extern "C" const uint64_t* tasr_get_dropout_seed_ptr(void) {
+  return reinterpret_cast<const uint64_t*>(g_tasr_seed_ptr);
+}
+
 extern "C" uint64_t tasr_launch_count(void) { return g_tasr_launches; }
 
 int tasr_set_cuda_error(cudaError_t e) {

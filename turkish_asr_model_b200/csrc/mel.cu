@@ -319,11 +319,11 @@ extern "C" int tasr_mel_forward(const float* wave, int64_t wave_ld, const int32_
   if (e != cudaSuccess) return tasr_set_cuda_error(e);
 
   const size_t smem = (size_t)RAW * 4 + NFFT * 4 + NFFT * 8 + (size_t)FR * ZLD * 8 + (size_t)FR * PLD * 4 + 2 * 128 * 4 + 200 * 2 + 16;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static TasrPerDevice attr_done;
+  if (!attr_done.get()) {
     e = cudaFuncSetAttribute(mel_logpower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tasr_set_cuda_error(e);
-    attr_done = true;
+    attr_done.set();
   }
   dim3 g1(cdiv(Tmax, FR), B);
   mel_logpower_kernel<<<g1, MEL_THREADS, smem, st>>>(wave, wave_ld, n_samples, window, fb, ranges, n_mels, feats, Tmax,

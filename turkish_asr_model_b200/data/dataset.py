@@ -47,18 +47,17 @@ class BucketingSampler(Sampler):
         self.epoch = epoch
 
     def _flat_order(self, bucket):
-        indices = sorted(range(len(self.lengths)), key=lambda i: self.lengths[i])
-        batches = []
-        for i in range(0, len(indices), bucket):
-            batch = indices[i:i + bucket]
-            if len(batch) == bucket or not self.drop_last:
-                batches.append(batch)
+        """Length-sorted index list cut into buckets of `bucket`, optionally shuffled as whole buckets.  The stable sort
+        and the single list shuffle consume the random stream exactly like the reference, so orders are bit-identical."""
+        n = len(self.lengths)
+        by_length = sorted(range(n), key=self.lengths.__getitem__)
+        buckets = [by_length[lo: lo + bucket] for lo in range(0, n, bucket)]
+        if self.drop_last and buckets and len(buckets[-1]) < bucket:
+            buckets.pop()
         if self.shuffle:
-            if self.seed is None:
-                random.shuffle(batches)
-            else:
-                random.Random(self.seed + self.epoch).shuffle(batches)
-        return batches
+            rng = random if self.seed is None else random.Random(self.seed + self.epoch)
+            rng.shuffle(buckets)
+        return buckets
 
     def __iter__(self):
         if self.world_size == 1:
@@ -79,13 +78,19 @@ class BucketingSampler(Sampler):
 
 
 def collate_fn(batch: List[Tuple[torch.Tensor, torch.Tensor]]):
-    """reference data/dataset.py:283-312: zero-pad features to Tmax and targets to Smax, return true lengths."""
-    batch = [item for item in batch if item is not None and item[0] is not None]
-    if len(batch) == 0:
+    """Batch assembly with the contract of reference data/dataset.py:283-312: items that failed to load (None) are
+    dropped; an empty batch yields four Nones; otherwise features (T_b, F) are zero-padded to the longest T and targets
+    (S_b,) to the longest S with id 0, and the true lengths come back as int64 vectors."""
+    kept = [(f, t) for item in batch if item is not None for (f, t) in [item] if f is not None]
+    if not kept:
         return None, None, None, None
-    features, targets = zip(*batch)
-    input_lengths = torch.LongTensor([f.size(0) for f in features])
-    target_lengths = torch.LongTensor([len(t) for t in targets])
-    features_padded = torch.nn.utils.rnn.pad_sequence(features, batch_first=True)
-    targets_padded = torch.nn.utils.rnn.pad_sequence(targets, batch_first=True, padding_value=0)
-    return features_padded, targets_padded, input_lengths, target_lengths
+    n = len(kept)
+    frames = [int(f.shape[0]) for f, _ in kept]
+    labels = [int(t.shape[0]) for _, t in kept]
+    f0, t0 = kept[0]
+    feats = f0.new_zeros((n, max(frames)) + tuple(f0.shape[1:]))
+    targets = t0.new_zeros((n, max(labels)) + tuple(t0.shape[1:]))
+    for b, (f, t) in enumerate(kept):
+        feats[b, : frames[b]] = f
+        targets[b, : labels[b]] = t
+    return feats, targets, torch.tensor(frames, dtype=torch.int64), torch.tensor(labels, dtype=torch.int64)

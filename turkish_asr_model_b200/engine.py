@@ -95,6 +95,14 @@ class FlatParams:
                 p.data = view
                 self._ptrs[name] = view.data_ptr()
         self.shadow_fresh = False
+        self._plist = [named[n] for n in self.names]
+        self._cast_version = -1
+
+    def param_version(self):
+        """Sum of the autograd version counters of every parameter: any in-place edit made through PyTorch
+        (torch.optim step on the autograd path, load_state_dict, p.data.copy_ ...) bumps it.  The fused AdamW
+        kernel writes params and shadow together through raw pointers and therefore leaves it untouched."""
+        return sum(p._version for p in self._plist)
 
     def still_valid(self):
         p = self.model.fc.weight
@@ -106,9 +114,14 @@ class FlatParams:
         return buf[self.offsets[name]: self.offsets[name] + n].view(p_shape)
 
     def refresh_shadow(self):
-        if not self.shadow_fresh:
+        """Re-cast the bf16 GEMM operands when the fp32 parameters were changed behind the engine's back."""
+        v = self.param_version()
+        if not self.shadow_fresh or v != self._cast_version:
+            if torch.cuda.is_current_stream_capturing():
+                raise L.TasrError("parameters changed during CUDA-graph capture")
             L.cast_bf16(self.params, out=self.shadow)
             self.shadow_fresh = True
+            self._cast_version = v
 
     def grad_views(self):
         """name -> view into the flat gradient buffer (dead parameters excluded)."""
@@ -184,6 +197,16 @@ class ConformerEngine:
 
         self.P, self.S, self.Gv = P, S, G
         self.qkv_w_shape = (d + 2 * DH, d)
+
+    def workspace_bytes(self, B, T, smax):
+        """Largest scratch request any kernel of one training step makes for a batch of B utterances of T mel frames
+        and targets padded to smax (the shared scratch buffer must have this size BEFORE a CUDA-graph capture)."""
+        lib = L.lib()
+        _, _, T2, _ = L.sub_dims(T, 80)
+        M = B * T2
+        return max(lib.tasr_groupnorm_workspace_bytes(B, T2, self.d), lib.tasr_bn_bwd_workspace_bytes(M, self.d),
+                   lib.tasr_mqa_attention_bwd_workspace_bytes(B, T2, self.H, self.d),
+                   lib.tasr_ctc_workspace_bytes(B, T2, self.V, max(int(smax), 1)), 1)
 
     def cos_sin(self, T, device):
         if self._cos_sin is None or self._cos_sin.shape[0] < T or self._cos_sin.device != device:
@@ -431,8 +454,16 @@ class ConformerEngine:
         on_segment_done(k) is called after the kernels producing gradient segment k have been enqueued
         (k = 0: classifier, 1..n: blocks n-1..0, n+1: subsampler) so that a data-parallel caller can start
         that segment's all-reduce while the rest of backward runs."""
+        dx0 = self.backward_blocks(tape, dlogits, on_segment_done)
+        self.backward_head(tape, dx0)
+        if on_segment_done is not None:
+            on_segment_done(1 + self.n_blocks)
+
+    def backward_blocks(self, tape, dlogits, on_segment_done=None):
+        """Classifier + Conformer blocks (95 % of the gradient bytes).  Returns the bf16 gradient w.r.t. the
+        input_proj output, the operand of backward_head()."""
         P, S, Gv = self.P, self.S, self.Gv
-        d, V, F2 = self.d, self.V, self.F2
+        d, V = self.d, self.V
         B, T2, M = tape["B"], tape["T2"], tape["M"]
         dev = dlogits.device
         Vp = _align(V)
@@ -456,9 +487,16 @@ class ConformerEngine:
             dx0 = self._block_backward(i, dres, tape["blocks"][i], B, T2, tape["key_len"], cs, tape["drop"])
             if on_segment_done is not None:
                 on_segment_done(1 + k)
-        # input_proj + subsampler (model/conformer.py:177-185)
         if dx0 is None:  # no blocks
             dx0 = L.cast_bf16(dres)
+        return dx0
+
+    def backward_head(self, tape, dx0):
+        """input_proj + Conv2d subsampler (model/conformer.py:177-185)."""
+        P, Gv = self.P, self.Gv
+        d, F2 = self.d, self.F2
+        B, M = tape["B"], tape["M"]
+        dev = dx0.device
         y2v = tape["y2"].view(M, F2 * d)
         self._wgrad_bias(dx0, y2v, d, F2 * d, M, Gv("input_proj.weight"), Gv("input_proj.bias"), remap=(d, F2))
         Mpix = M * F2
@@ -473,5 +511,3 @@ class ConformerEngine:
         L.conv1_bwd(dy1, tape["feats"], P("subsample.0.weight"), P("subsample.0.bias"),
                     Gv("subsample.0.weight"), Gv("subsample.0.bias"))
         self._join()
-        if on_segment_done is not None:
-            on_segment_done(1 + self.n_blocks)

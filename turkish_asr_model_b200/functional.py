@@ -41,7 +41,11 @@ class _EncoderFn(torch.autograd.Function):
 def model_forward(model, x, input_lengths):
     L.require_cuda(x)
     eng = model.engine()
-    eng.ensure_flat()
+    flat = eng.ensure_flat()
+    # Drop-in autograd path: the weights may have been edited by anything between two calls (torch.optim step,
+    # load_state_dict, p.data.copy_ -- the last one is invisible to version counters), so the bf16 GEMM operands are
+    # re-cast on every call (one pass over the parameters, ~0.1 GB).  The Trainer path keeps them fresh itself.
+    flat.shadow_fresh = False
     params = tuple(model.parameters())
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     return _EncoderFn.apply(model, x, input_lengths, need_grad, *params)

@@ -102,6 +102,14 @@ class TurkishASRModel(nn.Module):
         self.n_heads = n_heads
         self.dropout_p = dropout
         self._engine = None
+        self.register_load_state_dict_post_hook(TurkishASRModel._invalidate_operands)
+
+    @staticmethod
+    def _invalidate_operands(module, incompatible_keys):
+        """load_state_dict rewrote the fp32 parameters: the engine's bf16 operand copies are stale."""
+        eng = module._engine
+        if eng is not None and eng.flat is not None:
+            eng.flat.shadow_fresh = False
 
     def engine(self):
         if self._engine is None:
