@@ -271,6 +271,40 @@ int tasr_clip_adamw(float* p, const float* g, float* m, float* v, void* shadow_b
 int tasr_argmax_collapse(const void* logits, int logits_bf16, int64_t ld, int B, int T, int V, const int64_t* lengths, int blank,
                          int64_t* ids, int64_t* tokens, int32_t* out_len, tasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * fp32 operand mode of the encoder forward (csrc/fp32_mode.cu; north_star "1e-4 in fp32 mode").
+ * Replaces, for callers that ask for fp32 results: model/conformer.py:172-211 and model/attention.py:195-251 as they
+ * run WITHOUT autocast (trainer/trainer.py:227-282 validate on CPU, inference.py:101-128, BASELINE configs[0]).
+ * The contractions still run on tasr_gemm_bf16: an fp32 operand is expanded into bf16 pieces x = h0 + h1 + h2 and the
+ * product terms are concatenated along K (A' = [a0|a0|a1..], B' = [b0|b1|b0..]), K' = nterms * K.
+ *   terms: 4 bits per term, term t uses piece (terms >> 4t) & 15; nterms in 1..6.
+ *   split_terms: out (M, nterms*K) bf16 from in (M, K [or 2K for act 2/3]) fp32 with row pitch ld_in;
+ *                act 0 none | 1 silu | 2 silu(in[:, :K]) * in[:, K:] | 3 in[:, :K] * sigmoid(in[:, K:]);
+ *                remap_q > 0: destination column (c % q) * (K / q) + c / q (same packing as pack_weight_remap).
+ *   conv1      : x (B,T,F) -> y1 (B,T1,F1,d) fp32 channels-last = silu(conv1(x)).
+ *   im2col_split: y1 -> (B*T2*F2, nterms*9d) bf16, column t*9d + (kh*3+kw)*d + c (conv2's operand).
+ *   rope       : in place on the first rot_cols (multiple of 64) fp32 columns of qkv (M, ld); cos_sin (>=T, 32, 2).
+ *   mqa_fwd    : qkv (B*T, d+128) fp32 = [q heads | k | v] -> ctx (B*T, d) fp32; key_lengths (B) int64 or NULL.
+ *   dwconv31   : u (B,T,d) fp32 -> out fp32 (+bias); bn_partial (tasr_f32_dwconv_parts(B,T), d, 2) sums or NULL.
+ *   bn_silu    : out = silu((w - mean) * rstd * gamma + beta) with stats (d,2) from tasr_bn_finalize.
+ * ---------------------------------------------------------------------------------------------- */
+int tasr_f32_split_terms(const float* in, int64_t M, int K, int64_t ld_in, int act, int remap_q, uint32_t terms, int nterms,
+                         void* out, tasr_stream_t stream);
+int tasr_f32_conv1(const float* x, int B, int T, int F, int d, const float* w1, const float* b1, float* y1,
+                   tasr_stream_t stream);
+int tasr_f32_im2col_split(const float* y1, int B, int T, int F, int d, uint32_t terms, int nterms, void* out,
+                          tasr_stream_t stream);
+int tasr_f32_rope(float* qkv, int64_t M, int T, int ld, int rot_cols, const float* cos_sin, tasr_stream_t stream);
+int tasr_f32_mqa_fwd(const float* qkv, int B, int T, int H, int d, const int64_t* key_lengths, float* ctx,
+                     tasr_stream_t stream);
+int tasr_f32_dwconv_parts(int B, int T);
+int tasr_f32_dwconv31(const float* u, int B, int T, int d, const float* weight, const float* bias, float* out,
+                      float* bn_partial, tasr_stream_t stream);
+int tasr_f32_bn_silu(const float* w, int64_t M, int d, const float* stats, const float* gamma, const float* beta,
+                     float* out, tasr_stream_t stream);
+/* u (M, d) = ab[:, :d] * sigmoid(ab[:, d:]) on a dense (M, 2d) fp32 matrix (nn.GLU, model/conformer.py:60,82). */
+int tasr_f32_glu(const float* ab, int64_t M, int d, float* u, tasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

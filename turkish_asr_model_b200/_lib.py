@@ -56,6 +56,15 @@ _SIGNATURES = {
     "tasr_grad_sumsq": (I, [P, L, P, P]),
     "tasr_clip_adamw": (I, [P, P, P, P, P, L, P, P, P, P]),
     "tasr_argmax_collapse": (I, [P, I, L, I, I, I, P, I, P, P, P, P]),
+    "tasr_f32_split_terms": (I, [P, L, I, L, I, I, C.c_uint32, I, P, P]),
+    "tasr_f32_conv1": (I, [P, I, I, I, I, P, P, P, P]),
+    "tasr_f32_im2col_split": (I, [P, I, I, I, I, C.c_uint32, I, P, P]),
+    "tasr_f32_rope": (I, [P, L, I, I, I, P, P]),
+    "tasr_f32_mqa_fwd": (I, [P, I, I, I, I, P, P, P]),
+    "tasr_f32_dwconv_parts": (I, [I, I]),
+    "tasr_f32_dwconv31": (I, [P, I, I, I, P, P, P, P, P]),
+    "tasr_f32_bn_silu": (I, [P, L, I, P, P, P, P, P]),
+    "tasr_f32_glu": (I, [P, L, I, P, P]),
 }
 
 
@@ -471,3 +480,81 @@ def specaugment_(feats, params, frames=None):
     B, T, F = feats.shape
     check(lib().tasr_specaugment(ptr(feats), B, T, F, ptr(params), params.shape[1], ptr(frames), stream_ptr()))
     return feats
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32 operand mode (csrc/fp32_mode.cu): bf16 piece expansion around the same tcgen05 GEMM
+# ---------------------------------------------------------------------------------------------
+# piece indices per product term, A side / B side: sum_t A_piece[t] * B_piece[t]
+F32_TERMS = {3: ((0, 0, 1), (0, 1, 0)), 6: ((0, 0, 1, 0, 1, 2), (0, 1, 0, 2, 1, 0))}
+ACT_NONE, ACT_SILU, ACT_SWIGLU, ACT_GLU = range(4)
+
+
+def _pack_terms(pieces):
+    v = 0
+    for t, p in enumerate(pieces):
+        v |= p << (4 * t)
+    return v
+
+
+def f32_split(x2d, K, side, nterms=3, act=ACT_NONE, remap_q=0):
+    """x2d (M, K or 2K) fp32 (row pitch = stride(0)) -> (M, nterms*K) bf16 operand of the expanded GEMM.
+    side 0 = A (activations), 1 = B (weights)."""
+    require_cuda(x2d)
+    M = x2d.shape[0]
+    out = torch.empty(M, nterms * K, dtype=torch.bfloat16, device=x2d.device)
+    check(lib().tasr_f32_split_terms(ptr(x2d), M, K, x2d.stride(0), act, remap_q, _pack_terms(F32_TERMS[nterms][side]), nterms,
+                                     ptr(out), stream_ptr()))
+    return out
+
+
+def f32_conv1(x, w1, b1):
+    B, T, F = x.shape
+    d = w1.shape[0]
+    T1, F1, _, _ = sub_dims(T, F)
+    y1 = torch.empty(B, T1, F1, d, dtype=torch.float32, device=x.device)
+    check(lib().tasr_f32_conv1(ptr(x), B, T, F, d, ptr(w1), ptr(b1), ptr(y1), stream_ptr()))
+    return y1
+
+
+def f32_im2col_split(y1, T, F, nterms=3):
+    B, _, _, d = y1.shape
+    _, _, T2, F2 = sub_dims(T, F)
+    out = torch.empty(B * T2 * F2, nterms * 9 * d, dtype=torch.bfloat16, device=y1.device)
+    check(lib().tasr_f32_im2col_split(ptr(y1), B, T, F, d, _pack_terms(F32_TERMS[nterms][0]), nterms, ptr(out), stream_ptr()))
+    return out
+
+
+def f32_rope_(qkv, T, rot_cols, cos_sin):
+    check(lib().tasr_f32_rope(ptr(qkv), qkv.shape[0], T, qkv.stride(0), rot_cols, ptr(cos_sin), stream_ptr()))
+
+
+def f32_mqa_fwd(qkv, B, T, H, d, key_lengths):
+    _check_key_lengths(key_lengths, B)
+    ctx = torch.empty(B * T, d, dtype=torch.float32, device=qkv.device)
+    check(lib().tasr_f32_mqa_fwd(ptr(qkv), B, T, H, d, ptr(key_lengths), ptr(ctx), stream_ptr()))
+    return ctx
+
+
+def f32_dwconv(u, weight, bias, want_stats):
+    B, T, d = u.shape
+    out = torch.empty_like(u)
+    part = torch.empty(lib().tasr_f32_dwconv_parts(B, T), d, 2, dtype=torch.float32, device=u.device) if want_stats else None
+    check(lib().tasr_f32_dwconv31(ptr(u), B, T, d, ptr(weight), ptr(bias), ptr(out), ptr(part), stream_ptr()))
+    return out, part
+
+
+def f32_bn_silu(w, stats, gamma, beta):
+    M, d = w.numel() // w.shape[-1], w.shape[-1]
+    out = torch.empty_like(w)
+    check(lib().tasr_f32_bn_silu(ptr(w), M, d, ptr(stats), ptr(gamma), ptr(beta), ptr(out), stream_ptr()))
+    return out
+
+
+def f32_glu(ab, d):
+    M = ab.shape[0]
+    if ab.stride(0) != 2 * d:
+        raise TasrError("f32_glu needs a dense (M, 2d) matrix")
+    u = torch.empty(M, d, dtype=torch.float32, device=ab.device)
+    check(lib().tasr_f32_glu(ptr(ab), M, d, ptr(u), stream_ptr()))
+    return u

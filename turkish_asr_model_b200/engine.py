@@ -165,6 +165,10 @@ class ConformerEngine:
         self._side = None
         self._side_busy = False
         self._keep = []
+        # "bf16" (default: bf16 operands, the training path) or "fp32" (forward only: fp32 activations, contractions
+        # evaluated from bf16 piece expansions of the fp32 operands, logits within 1e-4 of the reference's fp32 run)
+        self.precision = "bf16"
+        self.f32_terms = 3  # 3 = a0b0+a0b1+a1b0 (~2^-17 per product); 6 adds the 2^-24 terms
 
     # ------------------------------------------------------------------ parameters
     def ensure_flat(self):
@@ -335,6 +339,96 @@ class ConformerEngine:
                       st3=st3, ab=ab, u=u, w=w, bnst=bnst, s=s, x3=x3, xn4=xn4, st4=st4, x4=x4, st5=st5, seed=seed)
             tape["blocks"].append(sv)
         return x5.view(M, d)
+
+    # ------------------------------------------------------------------ fp32 operand mode (forward only)
+    def forward_f32(self, feats, input_lengths, training):
+        """Same forward as forward(), for callers that want fp32 results (reference without autocast:
+        trainer/trainer.py:227-282, inference.py:101-128, the CPU run of BASELINE configs[0]).  Activations stay fp32;
+        every Linear / Conv is the tcgen05 GEMM on bf16 piece expansions of its fp32 operands (csrc/fp32_mode.cu).
+        Returns logits (B, T', V) fp32.  No tape: backward is not available in this mode."""
+        if training and self.model.dropout_p > 0.0:
+            raise L.TasrError("fp32 mode models no dropout: use eval mode or dropout=0.0")
+        f = self.ensure_flat()
+        P = self.P
+        d, dff, H, G, V, nt = self.d, self.dff, self.H, self.G, self.V, self.f32_terms
+        B, T, F = feats.shape
+        feats = feats.contiguous().float()
+        T1, F1, T2, F2 = L.sub_dims(T, F)
+        if F2 != self.F2:
+            raise L.TasrError("n_mel_channels mismatch: input_proj expects %d frequency bins after subsampling" % self.F2)
+        M = B * T2
+        dev = feats.device
+        key_len = None
+        if input_lengths is not None:
+            key_len = (input_lengths.to(device=dev, dtype=torch.int64) // 4).contiguous()
+        cs = self.cos_sin(T2, dev)
+
+        def linear(a_split, w2d, bias, n, k, out=None, resid=None, alpha=1.0, remap_q=0):
+            """out (rows, n) fp32 = a @ w^T + bias (+ residual); a_split is the expanded A operand (rows, nt*k)."""
+            wb = L.f32_split(w2d, k, 1, nt, remap_q=remap_q)
+            rows = a_split.shape[0]
+            ldo = (n + 3) // 4 * 4
+            if out is None:
+                out = torch.empty(rows, ldo, dtype=torch.float32, device=dev)
+            if resid is None:
+                L.gemm(rows, n, nt * k, a_split, nt * k, wb, nt * k, L.EPI_STORE, out, ldo, out_f32=1, bias=bias)
+            else:
+                L.gemm(rows, n, nt * k, a_split, nt * k, wb, nt * k, L.EPI_RESID, out, ldo, bias=bias, aux=resid, ldaux=n,
+                       alpha=alpha)
+            return out
+
+        # ---- subsampler (model/conformer.py:177-185)
+        y1 = L.f32_conv1(feats, P("subsample.0.weight"), P("subsample.0.bias"))
+        col = L.f32_im2col_split(y1, T, F, nt)
+        del y1
+        # conv2 weight (co, ci, kh, kw) -> (co, kh, kw, ci): the im2col column order
+        z2 = linear(col, P("subsample.2.weight").view(d, 9 * d), P("subsample.2.bias"), d, 9 * d, remap_q=9)
+        del col
+        a = L.f32_split(z2.view(M, F2 * d), F2 * d, 0, nt, act=L.ACT_SILU)  # SiLU, rows (b,t'), columns (f', c)
+        del z2
+        x = linear(a, P("input_proj.weight"), P("input_proj.bias"), d, F2 * d, remap_q=F2)
+        del a
+
+        for i in range(self.n_blocks):
+            pre = "blocks.%d." % i
+
+            def gn(t, name):
+                y, _ = L.groupnorm_fwd(t.view(B, T2, d), G, P(pre + name + ".weight"), P(pre + name + ".bias"), out_bf16=False)
+                return y.view(M, d)
+
+            def ff(t, name, norm):
+                h1 = linear(L.f32_split(gn(t, norm), d, 0, nt), P(pre + name + "linear1.weight"), P(pre + name + "linear1.bias"),
+                            2 * dff, d)
+                return linear(L.f32_split(h1, dff, 0, nt, act=L.ACT_SWIGLU), P(pre + name + "linear2.weight"),
+                              P(pre + name + "linear2.bias"), d, dff, resid=t, alpha=0.5)
+
+            x = ff(x, "ff1.", "norm_ff1.norm")
+            # attention (model/attention.py:195-251): fused q|k|v projection, RoPE on q and k, MQA core, output projection
+            qkv = linear(L.f32_split(gn(x, "norm_attn.norm"), d, 0, nt), P(pre + "attn.linear_q.weight", self.qkv_w_shape),
+                         P(pre + "attn.linear_q.bias", (d + 2 * DH,)), d + 2 * DH, d)
+            L.f32_rope_(qkv, T2, d + DH, cs)
+            ctx = L.f32_mqa_fwd(qkv, B, T2, H, d, key_len)
+            x = linear(L.f32_split(ctx, d, 0, nt), P(pre + "attn.linear_out.weight"), P(pre + "attn.linear_out.bias"), d, d,
+                       resid=x, alpha=1.0)
+            # conv module (model/conformer.py:76-88)
+            ab = linear(L.f32_split(gn(x, "conv.norm.norm"), d, 0, nt), P(pre + "conv.pointwise_conv1.weight", (2 * d, d)),
+                        P(pre + "conv.pointwise_conv1.bias"), 2 * d, d)
+            u = L.f32_glu(ab, d)  # the depthwise conv needs the fp32 activation itself, not an expanded operand
+            w, part = L.f32_dwconv(u.view(B, T2, d), P(pre + "conv.depthwise_conv.weight", (d, 31)),
+                                   P(pre + "conv.depthwise_conv.bias"), want_stats=training)
+            bn = self.model.blocks[i].conv.batch_norm
+            bnst = L.bn_finalize(part, d, M, bn.eps, bn.momentum if bn.momentum is not None else 0.1, training,
+                                 bn.running_mean, bn.running_var, bn.num_batches_tracked)
+            sact = L.f32_bn_silu(w, bnst, P(pre + "conv.batch_norm.weight"), P(pre + "conv.batch_norm.bias"))
+            x = linear(L.f32_split(sact.view(M, d), d, 0, nt), P(pre + "conv.pointwise_conv2.weight", (d, d)),
+                       P(pre + "conv.pointwise_conv2.bias"), d, d, resid=x, alpha=1.0)
+            x = ff(x, "ff2.", "norm_ff2.norm")
+            x = gn(x, "final_norm.norm")
+
+        Vp = (V + 3) // 4 * 4
+        logits = torch.zeros(M, Vp, dtype=torch.float32, device=dev) if Vp != V else torch.empty(M, Vp, dtype=torch.float32, device=dev)
+        linear(L.f32_split(x, d, 0, nt), P("fc.weight"), P("fc.bias"), V, d, out=logits)
+        return logits.view(B, T2, Vp)[:, :, :V]
 
     # ------------------------------------------------------------------ backward
     def ensure_side_stream(self, device):

@@ -48,6 +48,11 @@ def model_forward(model, x, input_lengths):
     flat.shadow_fresh = False
     params = tuple(model.parameters())
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    if eng.precision == "fp32":
+        if need_grad:
+            raise L.TasrError("fp32 operand mode is forward-only: call the model under torch.no_grad() (training runs "
+                              "in the bf16 operand mode)")
+        return eng.forward_f32(x, input_lengths, model.training)
     return _EncoderFn.apply(model, x, input_lengths, need_grad, *params)
 
 

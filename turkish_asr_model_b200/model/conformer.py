@@ -111,6 +111,14 @@ class TurkishASRModel(nn.Module):
         if eng is not None and eng.flat is not None:
             eng.flat.shadow_fresh = False
 
+    def set_precision(self, precision: str):
+        """"bf16" (default; bf16 GEMM operands, training + inference) or "fp32" (forward only; fp32 activations and
+        fp32-accurate contractions, logits within 1e-4 of the reference's fp32 run)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.engine().precision = precision
+        return self
+
     def engine(self):
         if self._engine is None:
             from ..engine import ConformerEngine

@@ -468,7 +468,10 @@ class Trainer:
                     continue
                 features, targets, input_lengths, target_lengths = batch
                 il = input_lengths.to(dev, dtype=torch.int64)
-                logits, _ = eng.forward(features.to(dev), il, False, 0.0, save=False)
+                if eng.precision == "fp32":  # the reference validates in fp32 on CPU (trainer/trainer.py:227-282)
+                    logits = eng.forward_f32(features.to(dev), il, False)
+                else:
+                    logits, _ = eng.forward(features.to(dev), il, False, 0.0, save=False)
                 loss, _, _ = L.ctc_loss_fwd_bwd(logits, targets.to(dev), il // 4, target_lengths.to(dev, torch.int64),
                                                 blank=self.blank, want_grad=False)
                 total += float(loss)
