@@ -71,7 +71,9 @@ def make_epoch(n_utts=4096, seed=1234):
 def make_batches(n_batches, rank, world, seed=1234):
     """Bucketed batches exactly as the (rank-sharded) BucketingSampler yields them."""
     from turkish_asr_model_b200.data.dataset import BucketingSampler
-    n_samples = make_epoch(seed=seed)
+    # weak scaling: 4096 utterances per rank, so a (global) bucket spans the same 0.16 s of lengths at every N and the
+    # ranks' slices of it differ by less than that (no stragglers, same padding waste as at N = 1)
+    n_samples = make_epoch(n_utts=4096 * world, seed=seed)
     sizes = [44 + 2 * int(n) for n in n_samples]
     sampler = BucketingSampler(None, CFG["batch"], shuffle=True, drop_last=False, rank=rank, world_size=world, seed=seed,
                                lengths=sizes)
@@ -80,7 +82,8 @@ def make_batches(n_batches, rank, world, seed=1234):
     batches = []
     g = torch.Generator().manual_seed(seed + 17 + rank)
     for i in range(n_batches):
-        idx = flat[(i * B) % (len(flat) - B + 1): (i * B) % (len(flat) - B + 1) + B]
+        k = i % (len(flat) // B)  # whole batches only: a window never straddles two length buckets
+        idx = flat[k * B: (k + 1) * B]
         ns = n_samples[idx]
         tl = torch.round(4.0 * ns.double() / SR).to(torch.int64)
         smax = int(tl.max())

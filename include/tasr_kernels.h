@@ -99,6 +99,9 @@ typedef struct tasr_gemm_args {
   int32_t split_k;  /* ATOMIC only: number of splits of the reduction (>=1) */
   int32_t remap_p0; /* ATOMIC only: if >0, column n is written at (n % p0) * p1 + n / p0 */
   int32_t remap_p1;
+  float* colsum;    /* ATOMIC only, may be NULL: colsum[m] += alpha * sum_k A(m, k) -- for a wgrad (A = dy) this is the
+                       bias gradient, produced by one extra N = 16 UMMA per k-step against a tile of ones (replaces a
+                       separate column-sum pass over dy) */
 } tasr_gemm_args;
 
 int tasr_gemm_bf16(const tasr_gemm_args* args, tasr_stream_t stream);

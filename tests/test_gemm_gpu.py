@@ -84,6 +84,23 @@ def test_gemm_wgrad_splitk_remap(cuda):
     assert (dW2.double().cpu() - ref2).abs().max().item() < 0.02 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("N,K,Mtok,split", [(256, 1024, 5000, 4), (1000, 256, 2008, 7), (384, 256, 777, 1), (2048, 256, 3000, 9)])
+def test_gemm_wgrad_with_fused_bias_gradient(cuda, N, K, Mtok, split):
+    """ATOMIC epilogue with `colsum`: the bias gradient sum_tokens dy[t, o] comes out of the same pass over dy (an extra
+    N = 16 UMMA against a tile of ones), for wide / narrow tiles, ragged out-feature counts and any split count."""
+    g = torch.Generator().manual_seed(N + K + split)
+    dy = torch.randn(Mtok, N, generator=g).to(torch.bfloat16).to(cuda)
+    x = torch.randn(Mtok, K, generator=g).to(torch.bfloat16).to(cuda)
+    dW = torch.zeros(N, K, device=cuda)
+    db = torch.full((N,), 0.5, device=cuda)  # accumulates (+=)
+    L.gemm(N, K, Mtok, dy, N, x, K, L.EPI_ATOMIC, dW, K, a_mn=1, b_mn=1, split_k=split, colsum=db)
+    torch.cuda.synchronize()
+    ref = dy.double().cpu().t() @ x.double().cpu()
+    assert (dW.double().cpu() - ref).abs().max().item() < 0.02 * ref.abs().max().item()
+    ref_b = 0.5 + dy.double().cpu().sum(0)
+    assert (db.double().cpu() - ref_b).abs().max().item() < 2e-3 * ref_b.abs().max().item()
+
+
 def test_gemm_resid(cuda):
     M, N, K = 777, 256, 1024
     g = torch.Generator().manual_seed(11)

@@ -16,6 +16,8 @@ T1, F1 = (T - 1) // 2 + 1, (F - 1) // 2 + 1
 Tp = (T1 - 1) // 2 + 1
 M = B * Tp
 sel = sys.argv[1:]
+# BK_FLUSH=1: write a 512 MB buffer between launches, so every launch sees cold operands (HBM, not L2) like inside a step
+_flush = torch.empty(128 << 20, dtype=torch.float32, device=dev) if os.environ.get("BK_FLUSH", "0") == "1" else None
 
 
 def timeit(name, fn, bytes_=0, iters=int(os.environ.get("BK_ITERS", "10"))):
@@ -26,6 +28,8 @@ def timeit(name, fn, bytes_=0, iters=int(os.environ.get("BK_ITERS", "10"))):
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:   # device time only (these calls are host-bound from python)
         for _ in range(iters):
+            if _flush is not None:
+                _flush.fill_(0.0)
             fn()
         torch.cuda.synchronize()
     evs = [ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and "at::native" not in ev.name]

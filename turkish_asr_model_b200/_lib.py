@@ -161,12 +161,13 @@ class GemmArgs(C.Structure):
         ("seed", C.c_uint64),
         ("split_k", C.c_int32),
         ("remap_p0", C.c_int32), ("remap_p1", C.c_int32),
+        ("colsum", C.c_void_p),
     ]
 
 
 def gemm(M, N, K, A, lda, B, ldb, epilogue, out, ldo, a_mn=0, b_mn=0, out_f32=0, out2=None, ldo2=0,
          bias=None, aux=None, ldaux=0, alpha=1.0, n_half=0, drop_p=0.0, seed=0, split_k=1,
-         remap_p0=0, remap_p1=0):
+         remap_p0=0, remap_p1=0, colsum=None):
     require_cuda(A, B, out)
     a = GemmArgs()
     a.M, a.N, a.K = M, N, K
@@ -179,6 +180,7 @@ def gemm(M, N, K, A, lda, B, ldb, epilogue, out, ldo, a_mn=0, b_mn=0, out_f32=0,
     a.aux, a.ldaux = (aux.data_ptr() if aux is not None else 0), ldaux
     a.alpha, a.n_half, a.drop_p, a.seed = alpha, n_half, drop_p, seed
     a.split_k, a.remap_p0, a.remap_p1 = split_k, remap_p0, remap_p1
+    a.colsum = colsum.data_ptr() if colsum is not None else 0
     fn = lib().tasr_gemm_bf16
     if GEMM_PROFILE is not None:  # bench.py roofline pass: remember every tcgen05 GEMM launch of a step
         nb = 2 if epilogue in (EPI_SWIGLU, EPI_GLU) else 1

@@ -425,6 +425,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= 2ull << 61;  // SWIZZLE_128B
   return d;
 }
+// Same, no swizzle (layout type 0), K-major: core matrices of 8 rows x 16 B stored contiguously (128 B each);
+// LBO = bytes between core matrices adjacent along K, SBO = bytes between 8-row groups along M|N.
+__device__ __forceinline__ uint64_t umma_desc_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // version = 1 (Blackwell)
+  return d;
+}
 // UMMA instruction descriptor: bf16 x bf16 -> fp32, M x N tile, per-operand major-ness (0 = K, 1 = MN)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4)                       // D format: fp32

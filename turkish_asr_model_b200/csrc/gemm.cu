@@ -30,7 +30,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr bool DUAL = (EPI == TASR_EPI_SWIGLU || EPI == TASR_EPI_GLU);
   constexpr int A_BYTES = BM * BK * 2;  // 16 KB
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulators
+  // Weight gradients (split-K, EPI_ATOMIC): a CTA gets one tile (the grid is one wave), so a single accumulator is
+  // enough; the 16 columns behind it hold the bias-gradient accumulator (A x ones).
+  constexpr bool WG = (EPI == TASR_EPI_ATOMIC);
+  constexpr int NACC = WG ? 1 : 2;
+  constexpr int ONES_BYTES = WG ? 512 : 0;
+  constexpr uint32_t TMEM_COLS = WG ? (BN + 16 <= 256 ? 256u : 512u) : 2u * BN;  // power of two
   constexpr int TILE_N = DUAL ? BN / 2 : BN;
   constexpr int NBUF = DUAL ? 3 : ((EPI == TASR_EPI_SILU || EPI == TASR_EPI_SWIGLU_BWD || EPI == TASR_EPI_GLU_BWD) ? 2 : 1);
   static_assert(RINGG >= NBUF, "staging ring too small");
@@ -40,7 +45,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint8_t* sC = sB + STAGES * B_BYTES;  // 2 groups x RINGG staging buffers
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sC + 2 * RINGG * STAGE_BYTES);
+  uint8_t* sOnes = sC + 2 * RINGG * STAGE_BYTES;  // WG: 16 (N) x 16 (K) bf16 ones as 4 un-swizzled core matrices
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
@@ -67,6 +73,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (WG) {
+    if (threadIdx.x < ONES_BYTES / 4) reinterpret_cast<uint32_t*>(sOnes)[threadIdx.x] = 0x3F803F80u;  // bf16 1.0 x 2
+    fence_proxy_async_smem();  // the tensor core reads shared memory through the async proxy
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -110,12 +120,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== UMMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_ones = umma_idesc_bf16(BM, 16, A_MN ? 1 : 0, 0);
+      const uint64_t ones_desc = umma_desc_noswizzle(smem_u32(sOnes), 128, 256);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const int split = tile / (p.tiles_n * p.tiles_m);
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
-        const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+        const uint32_t acc = NACC == 2 ? (tcount & 1u) : 0u, aph = NACC == 2 ? ((tcount >> 1) & 1u) : (tcount & 1u);
+        const bool do_colsum = WG && p.colsum != nullptr && (tile % p.tiles_n) == 0;
         mbar_wait_backoff(&tempty_bar[acc], aph ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -135,6 +148,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t bdesc = B_MN ? umma_desc_sw128(b_base + k * 2048, 8192, 1024)
                                         : umma_desc_sw128(b_base + k * 32, 16, 1024);
             umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            // bias gradient: the same A k-slice against ones -> sum over k of A(m, k) in 16 identical columns
+            if (do_colsum) umma_bf16(tmem_base + BN, adesc, ones_desc, idesc_ones, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
         }
@@ -164,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_tile = (tile / p.tiles_n) % p.tiles_m;
       const int m0 = m_tile * BM, n0 = n_tile * TILE_N;
       const int row = m0 + rloc;
-      const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+      const uint32_t acc = NACC == 2 ? (tcount & 1u) : 0u, aph = NACC == 2 ? ((tcount >> 1) & 1u) : (tcount & 1u);
       // saved-tensor operands of this thread's first column group: in flight while we wait for the accumulator
       AuxBf16 ax_first[2];
       AuxF32 res_first[2];
@@ -304,6 +319,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ring += NBUF;
         }
       }
+      if (WG && p.colsum != nullptr && n_tile == 0 && sg == 0 && hsel == 0) {  // one warp per TMEM lane quarter
+        uint32_t cs[16];
+        tmem_ld16(tmem_base + BN + ((uint32_t)(q * 32) << 16), cs);
+        tmem_ld_wait();
+        if (row < p.M) atomicAdd(p.colsum + row, __uint_as_float(cs[0]) * p.alpha);
+      }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);  // all 512 epilogue threads: this accumulator may be overwritten
     }
@@ -378,6 +399,8 @@ int fill_dev(const tasr_gemm_args* a, GemmDev* p, bool* dual) {
   p->seed = a->seed;
   p->seed_ptr = g_tasr_seed_ptr;
   p->remap_p0 = a->remap_p0; p->remap_p1 = a->remap_p1;
+  p->colsum = (a->epilogue == TASR_EPI_ATOMIC) ? a->colsum : nullptr;
+  if (a->colsum != nullptr && a->epilogue != TASR_EPI_ATOMIC) return TASR_ERR_SHAPE;
   const int num_kb = (a->K + BK - 1) / BK;
   int splits = (a->epilogue == TASR_EPI_ATOMIC && a->split_k > 1) ? a->split_k : 1;
   if (splits > num_kb) splits = num_kb;
@@ -390,7 +413,8 @@ int fill_dev(const tasr_gemm_args* a, GemmDev* p, bool* dual) {
 template <int EPI, int BN, int STAGES, int RINGG, bool A_MN, bool B_MN>
 int launch_tc(const tasr_gemm_args* a, GemmDev& p, cudaStream_t st) {
   constexpr bool DUAL = (EPI == TASR_EPI_SWIGLU || EPI == TASR_EPI_GLU);
-  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 2 * RINGG * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 2 * RINGG * STAGE_BYTES + (EPI == TASR_EPI_ATOMIC ? 512 : 0) +
+                       (2 * STAGES + 4) * 8 + 16 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget");
   constexpr int TILE_N = DUAL ? BN / 2 : BN;
   CUtensorMap tmA, tmB, tmO, tmO2;

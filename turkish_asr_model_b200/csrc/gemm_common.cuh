@@ -37,6 +37,7 @@ struct GemmDev {
   int splits;
   int remap_p0, remap_p1;
   int tiles_m, tiles_n;
+  float* colsum;
 };
 
 // W consecutive columns of one row (W = 16 or 32), vectorised when the chunk is full and 16-byte aligned

@@ -165,6 +165,7 @@ class ConformerEngine:
         self._side = None
         self._side_busy = False
         self._keep = []
+        self._lagging = None  # (event, tensors) of the previous block's leaf kernels, joined one block late
         # "bf16" (default: bf16 operands, the training path) or "fp32" (forward only: fp32 activations, contractions
         # evaluated from bf16 piece expansions of the fp32 operands, logits within 1e-4 of the reference's fp32 run)
         self.precision = "bf16"
@@ -461,19 +462,31 @@ class ConformerEngine:
             torch.cuda.current_stream().wait_event(ev)
             self._side_busy = False
         self._keep.clear()
+        self._lagging = None
+
+    def _join_lagging(self):
+        """End of a block's backward: instead of stalling the main chain until this block's last weight-gradient kernel
+        has run, wait for the PREVIOUS block's leaf kernels (long finished by now) and release that block's
+        temporaries; this block's are handed over to the next call (or to the final _join())."""
+        if not self._side_busy:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        prev = self._lagging
+        self._lagging = (ev, list(self._keep))
+        self._keep.clear()
+        if prev is not None:
+            torch.cuda.current_stream().wait_event(prev[0])
 
     def _wgrad_bias(self, dy, x, out_f, in_f, tokens, gw, gb, remap=None):
-        """gw += dy^T x, gb += column sums of dy: leaf kernels (side stream)."""
-        def run():
-            self._wgrad(dy, x, out_f, in_f, tokens, gw, remap=remap)
-            L.colsum_add(dy, gb)
-        self._leaf(run, dy, x)
+        """gw += dy^T x, gb += column sums of dy: one leaf kernel (side stream)."""
+        self._leaf(lambda: self._wgrad(dy, x, out_f, in_f, tokens, gw, remap=remap, gb=gb), dy, x)
 
-    def _wgrad(self, dy, x, out_f, in_f, tokens, gw, remap=None):
-        """gw (out_f, in_f) fp32 += dy^T x."""
+    def _wgrad(self, dy, x, out_f, in_f, tokens, gw, remap=None, gb=None):
+        """gw (out_f, in_f) fp32 += dy^T x; gb (out_f) fp32 += column sums of dy, from the same pass over dy."""
         p0, p1 = remap if remap is not None else (0, 0)
         L.gemm(out_f, in_f, tokens, dy, dy.stride(0), x, x.stride(0), L.EPI_ATOMIC, gw, in_f, a_mn=1, b_mn=1,
-               split_k=_split_k(out_f, in_f, tokens), remap_p0=p0, remap_p1=p1)
+               split_k=_split_k(out_f, in_f, tokens), remap_p0=p0, remap_p1=p1, colsum=gb)
 
     def _ff_backward(self, pre, dy, saved, xn, M, drop, seed):
         """Backward of x + 0.5*dropout(linear2(dropout(swiglu(linear1(xn))))); dy = bf16(0.5 * mask * dres);
@@ -540,7 +553,7 @@ class ConformerEngine:
         dxn = self._ff_backward(pre + "ff1.", dy, sv["ff1"], sv["xn1"].view(M, d), M, drop, seed + 0)
         # the gradient leaving block 0 feeds input_proj's backward GEMMs: emit its bf16 copy too
         out = gn_bwd(dxn, sv["x"], sv["st1"], "norm_ff1.norm", True, cast=(1.0, 0.0, 0) if i == 0 else None)
-        self._join()  # this block's weight gradients are complete (and its temporaries may be released)
+        self._join_lagging()  # weight gradients trail the main chain by up to one block (see backward_blocks)
         return out
 
     def backward(self, tape, dlogits, on_segment_done=None):
@@ -580,7 +593,9 @@ class ConformerEngine:
         for k, i in enumerate(reversed(range(self.n_blocks))):
             dx0 = self._block_backward(i, dres, tape["blocks"][i], B, T2, tape["key_len"], cs, tape["drop"])
             if on_segment_done is not None:
+                self._join()  # the caller's all-reduce of this segment must see the finished weight gradients
                 on_segment_done(1 + k)
+        self._join()
         if dx0 is None:  # no blocks
             dx0 = L.cast_bf16(dres)
         return dx0
