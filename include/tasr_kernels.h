@@ -73,7 +73,10 @@ enum tasr_epilogue {
   TASR_EPI_SWIGLU_BWD = 5, /* acc = dh; aux = g|v; out(bf16, 2*n_half wide) = dg|dv                      */
   TASR_EPI_GLU_BWD = 6,    /* acc = du; aux = a|b; out = da|db                                           */
   TASR_EPI_SILU_BWD = 7,   /* out(bf16) = acc * silu'(aux)                                               */
-  TASR_EPI_ATOMIC = 8      /* out_f32[m*ldo + remap(n)] += alpha*acc  (split-K wgrad)                    */
+  TASR_EPI_ATOMIC = 8,     /* out_f32[m*ldo + remap(n)] += alpha*acc  (split-K wgrad)                    */
+  TASR_EPI_ROPE = 9        /* out(bf16) = rope(acc + bias): rotary embedding (model/attention.py:62-70) on the 64-wide
+                              heads in columns [0, remap_p0) with position m % n_half, aux = cos|sin table (>= n_half,
+                              32, 2) fp32; columns >= remap_p0 are stored unrotated (the fused q|k|v projection)  */
 };
 
 typedef struct tasr_gemm_args {

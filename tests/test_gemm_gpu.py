@@ -152,3 +152,28 @@ def test_dropout_mask_gemm_epilogues_match_cast_kernel(cuda):
     torch.cuda.synchronize()
     assert torch.equal(h.float() != 0, dgv[:, dff:].float() != 0)
     assert abs((h.float() != 0).float().mean().item() - (1 - p)) < 0.01
+
+
+@pytest.mark.parametrize("d,H,B,T", [(256, 4, 3, 77), (512, 8, 2, 203)])
+def test_gemm_rope_epilogue(cuda, d, H, B, T):
+    """Fused q|k|v projection with the rotary embedding applied to the q and k heads in the epilogue, against
+    oracle.apply_rope (model/attention.py:62-70) on the fp64 projection; the v columns are stored unrotated."""
+    from oracle import conformer as oc
+    g = torch.Generator().manual_seed(d + T)
+    M, N = B * T, d + 128
+    x = torch.randn(M, d, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, d, generator=g) / d ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    cos, sin = oc.rope_tables(T, 64)
+    cs = torch.stack([cos[:, :32], sin[:, :32]], dim=-1).contiguous().to(cuda)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=cuda)
+    L.gemm(M, N, d, x.to(cuda), d, w.to(cuda), d, L.EPI_ROPE, out, N, bias=bias.to(cuda), aux=cs, n_half=T, remap_p0=d + 64)
+    torch.cuda.synchronize()
+    y = x.double() @ w.double().t() + bias.double()
+    q = y[:, :d].reshape(B, T, H, 64).transpose(1, 2)
+    k = y[:, d:d + 64].reshape(B, T, 1, 64).transpose(1, 2)
+    qr = oc.apply_rope(q, cos.double(), sin.double()).transpose(1, 2).reshape(M, d)
+    kr = oc.apply_rope(k, cos.double(), sin.double()).transpose(1, 2).reshape(M, 64)
+    ref = torch.cat([qr, kr, y[:, d + 64:]], 1)
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert err < 1.2e-2 * ref.abs().max().item(), err  # bf16 output rounding

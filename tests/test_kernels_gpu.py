@@ -324,6 +324,32 @@ def test_ctc_c2_shape(cuda):
     assert g_dev.float().sum(-1).abs().max().item() < 1e-3
 
 
+def test_ctc_long_targets(cuda):
+    """Long-form transcripts: more than 255 labels per utterance (the one-thread-per-state kernel covers 2*255+1 states;
+    beyond that the strided kernel takes over), fp32 logits, ragged lengths, one NaN-free infeasible sample."""
+    B, T, V = 3, 700, 40
+    g = torch.Generator().manual_seed(8)
+    logits = torch.randn(B, T, V, generator=g)
+    tl = torch.tensor([300, 260, 699])
+    targets = torch.randint(1, V, (B, 699), generator=g)
+    il = torch.tensor([700, 640, 700])  # sample 2: 699 labels with repeats cannot fit 700 frames -> infeasible
+    # checker: torch's own CTCLoss + autograd in fp64 on the CPU (the reference's call; oracle/ctc.py is pinned to it by
+    # tests/test_oracle_golden.py and is a pure-Python loop, too slow at this size)
+    lg = logits.double().requires_grad_(True)
+    lp = torch.nn.functional.log_softmax(lg, dim=-1).transpose(0, 1)
+    nll = torch.nn.functional.ctc_loss(lp, targets, il, tl, blank=0, reduction="none", zero_infinity=False)
+    loss_ref = torch.nn.functional.ctc_loss(lp, targets, il, tl, blank=0, reduction="mean", zero_infinity=True)
+    loss_ref.backward()
+    l_dev, nll_dev, g_dev = L.ctc_loss_fwd_bwd(logits.to(cuda), targets.to(cuda), il.to(cuda), tl.to(cuda))
+    torch.cuda.synchronize()
+    assert torch.isinf(nll[2]) and np.isinf(nll_dev[2].item())
+    assert abs(l_dev.item() - loss_ref.item()) <= 1e-3 * abs(loss_ref.item())
+    assert np.allclose(nll_dev.cpu().numpy()[:2], nll.detach().numpy()[:2], rtol=1e-4)
+    grad = lg.grad.numpy()
+    assert np.abs(g_dev.double().cpu().numpy() - grad).max() <= 1e-3 * np.abs(grad).max()
+    assert np.all(g_dev[2].cpu().numpy() == 0)
+
+
 # ------------------------------------------------------------------ optimizer / decode
 def test_clip_adamw(cuda):
     n = 100003

@@ -141,7 +141,8 @@ def require_cuda(*ts):
 # GEMM
 # ---------------------------------------------------------------------------------------------
 GEMM_PROFILE = None
-EPI_STORE, EPI_RESID, EPI_SWIGLU, EPI_GLU, EPI_SILU, EPI_SWIGLU_BWD, EPI_GLU_BWD, EPI_SILU_BWD, EPI_ATOMIC = range(9)
+(EPI_STORE, EPI_RESID, EPI_SWIGLU, EPI_GLU, EPI_SILU, EPI_SWIGLU_BWD, EPI_GLU_BWD, EPI_SILU_BWD, EPI_ATOMIC,
+ EPI_ROPE) = range(10)
 
 
 class GemmArgs(C.Structure):

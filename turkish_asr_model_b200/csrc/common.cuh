@@ -406,6 +406,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
 // while its predecessor drains; everything before this wait (barrier init, TMEM allocation, descriptor prefetch)
 // overlaps with the predecessor's tail, everything after it sees the predecessor's memory.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

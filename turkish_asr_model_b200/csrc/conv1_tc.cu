@@ -37,6 +37,7 @@ struct Conv1TcParams {
   const bf16* dy1;   // bwd in (npix, d)
   float* dw1;        // (d, 9)  +=
   float* db1;        // (d)     +=
+  int ch0;           // first of the 256 output channels this launch computes (d > 256: one launch per 256-channel chunk)
 };
 
 // byte offset of bf16 element (row r, col c) in a [rows x 64] tile with 128-byte rows and the TMA/UMMA 128 B swizzle
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_fwd_kernel(const __gri
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < 2 * P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
-  build_weight_tile(sW, p.w1, p.b1);
+  build_weight_tile(sW, p.w1 + p.ch0 * 9, p.b1 + p.ch0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_fwd_kernel(const __gri
       __syncthreads();  // output tile staged, patch i+2 written
       if (tid == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) tma_store_2d(&tmY, sYt + q * (TPIX * 128), q * 64, tile * TPIX);  // rows >= npix clipped
+        for (int q = 0; q < 4; ++q) tma_store_2d(&tmY, sYt + q * (TPIX * 128), p.ch0 + q * 64, tile * TPIX);  // rows >= npix clipped
         bulk_commit();
       }
     }
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const __gri
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < 2 * P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
-  build_weight_tile(sW, p.w1, p.b1);
+  build_weight_tile(sW, p.w1 + p.ch0 * 9, p.b1 + p.ch0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const __gri
   auto load_dy = [&](int tile) {  // thread 0: the tile's 128 x 256 gradient block (rows >= npix zero-filled)
     mbar_expect_tx(&bars[2], DZ_BYTES);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) tma_load_2d(sG + q * (TPIX * 128), &tmG, &bars[2], q * 64, tile * TPIX);
+    for (int q = 0; q < 4; ++q) tma_load_2d(sG + q * (TPIX * 128), &tmG, &bars[2], p.ch0 + q * 64, tile * TPIX);
   };
   const uint32_t tZ = tmem, tD = tmem + CD;  // D: two accumulators (channel halves) of 32 columns
   const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -347,8 +348,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const __gri
       tmem_ld_wait();
       const int ch = cq * 128 + rloc;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) atomicAdd(p.dw1 + ch * 9 + k, __uint_as_float(u[k]) + __uint_as_float(u[16 + k]));
-      atomicAdd(p.db1 + ch, __uint_as_float(u[9]));
+      for (int k = 0; k < 9; ++k) atomicAdd(p.dw1 + (p.ch0 + ch) * 9 + k, __uint_as_float(u[k]) + __uint_as_float(u[16 + k]));
+      atomicAdd(p.db1 + p.ch0 + ch, __uint_as_float(u[9]));
     }
   }
   tc_fence_before();
@@ -359,8 +360,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1_tc_bwd_kernel(const __gri
 typedef CUresult (*PFN_encodeTiledTc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-// (npix, 256) bf16 row-major, box 64 columns x 128 rows, 128 B swizzle
-int make_out_map(CUtensorMap* m, void* base, long long npix) {
+// (npix, d) bf16 row-major, box 64 columns x 128 rows, 128 B swizzle
+int make_out_map(CUtensorMap* m, void* base, long long npix, int d) {
   static PFN_encodeTiledTc enc = nullptr;
   if (!enc) {
     void* fn = nullptr;
@@ -370,8 +371,8 @@ int make_out_map(CUtensorMap* m, void* base, long long npix) {
       return TASR_ERR_CUDA;
     enc = reinterpret_cast<PFN_encodeTiledTc>(fn);
   }
-  cuuint64_t dims[2] = {(cuuint64_t)CD, (cuuint64_t)npix};
-  cuuint64_t strides[1] = {(cuuint64_t)CD * 2};
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)npix};
+  cuuint64_t strides[1] = {(cuuint64_t)d * 2};
   cuuint32_t box[2] = {64, TPIX};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -391,7 +392,7 @@ int tc_num_sms() {
 }
 
 bool fill(Conv1TcParams* p, const float* x, int B, int T, int F, int d, const float* w1, const float* b1) {
-  if (d != CD || B <= 0 || T <= 0 || F <= 0) return false;
+  if (d <= 0 || d % CD || B <= 0 || T <= 0 || F <= 0) return false;  // d = 256 (default), 512 (Conformer-M), ...
   p->x = x; p->B = B; p->T = T; p->F = F;
   p->T1 = (T - 1) / 2 + 1;
   p->F1 = (F - 1) / 2 + 1;
@@ -401,6 +402,7 @@ bool fill(Conv1TcParams* p, const float* x, int B, int T, int F, int d, const fl
   p->ntiles = (int)nt;
   p->w1 = w1; p->b1 = b1;
   p->y1 = nullptr; p->dy1 = nullptr; p->dw1 = nullptr; p->db1 = nullptr;
+  p->ch0 = 0;
   return true;
 }
 
@@ -415,7 +417,7 @@ int tasr_conv1_tc_fwd(const float* x, int B, int T, int F, int d, const float* w
   p.y1 = reinterpret_cast<bf16*>(y1);
   if (reinterpret_cast<uintptr_t>(y1) & 15) return TASR_ERR_SHAPE;
   CUtensorMap tmY;
-  if (make_out_map(&tmY, y1, p.npix) != TASR_OK) return TASR_ERR_CUDA;
+  if (make_out_map(&tmY, y1, p.npix, d) != TASR_OK) return TASR_ERR_CUDA;
   constexpr int SMEM = W_BYTES + 2 * P_BYTES + 2 * DZ_BYTES + 64 + 1024;
   static TasrPerDevice attr_done;
   if (!attr_done.get()) {
@@ -424,8 +426,10 @@ int tasr_conv1_tc_fwd(const float* x, int B, int T, int F, int d, const float* w
     attr_done.set();
   }
   const int grid = p.ntiles < tc_num_sms() ? p.ntiles : tc_num_sms();
-  conv1_tc_fwd_kernel<<<grid, TC_THREADS, SMEM, st>>>(tmY, p);
-  TASR_CHECK_LAUNCH();
+  for (p.ch0 = 0; p.ch0 < d; p.ch0 += CD) {  // output channels are independent: one launch per 256-channel chunk
+    conv1_tc_fwd_kernel<<<grid, TC_THREADS, SMEM, st>>>(tmY, p);
+    TASR_CHECK_LAUNCH();
+  }
   return TASR_OK;
 }
 
@@ -438,7 +442,7 @@ int tasr_conv1_tc_bwd(const void* dy1, const float* x, int B, int T, int F, int 
   p.db1 = db1;
   if (reinterpret_cast<uintptr_t>(dy1) & 15) return TASR_ERR_SHAPE;
   CUtensorMap tmG;
-  if (make_out_map(&tmG, const_cast<void*>(dy1), p.npix) != TASR_OK) return TASR_ERR_CUDA;
+  if (make_out_map(&tmG, const_cast<void*>(dy1), p.npix, d) != TASR_OK) return TASR_ERR_CUDA;
   constexpr int SMEM = W_BYTES + 2 * P_BYTES + 2 * DZ_BYTES + 64 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget");
   static TasrPerDevice attr_done;
@@ -448,7 +452,9 @@ int tasr_conv1_tc_bwd(const void* dy1, const float* x, int B, int T, int F, int 
     attr_done.set();
   }
   const int grid = p.ntiles < tc_num_sms() ? p.ntiles : tc_num_sms();
-  conv1_tc_bwd_kernel<<<grid, TC_THREADS, SMEM, st>>>(tmG, p);
-  TASR_CHECK_LAUNCH();
+  for (p.ch0 = 0; p.ch0 < d; p.ch0 += CD) {
+    conv1_tc_bwd_kernel<<<grid, TC_THREADS, SMEM, st>>>(tmG, p);
+    TASR_CHECK_LAUNCH();
+  }
   return TASR_OK;
 }

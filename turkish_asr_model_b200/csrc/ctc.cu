@@ -157,6 +157,83 @@ __global__ void ctc_alpha_beta_kernel(int T, int Smax, const long long* __restri
   }
 }
 
+// Same recursion for targets longer than 255 labels (more than 1024 lattice states for both directions): 512 threads
+// per direction, each walking its states with a stride.  Long-form transcripts only; not tuned.
+__global__ void __launch_bounds__(1024) ctc_alpha_beta_long_kernel(int T, int Smax, const long long* __restrict__ targets,
+                                                                   const long long* __restrict__ in_len,
+                                                                   const long long* __restrict__ tgt_len, int blank, int V,
+                                                                   const float* __restrict__ lp, float* __restrict__ alpha,
+                                                                   float* __restrict__ beta, float* __restrict__ nll_out,
+                                                                   float* __restrict__ loss, int B,
+                                                                   unsigned short* __restrict__ slot_of_class,
+                                                                   int* __restrict__ first_occ, int NSP) {
+  extern __shared__ float sh_ab[];  // [2 dirs][2 buffers][NSP + 2]
+  const int b = blockIdx.x;
+  const int NTD = blockDim.x >> 1;
+  const int dir = threadIdx.x >= NTD ? 1 : 0;
+  const int tid = threadIdx.x - dir * NTD;
+  const int S = (int)tgt_len[b];
+  const int L = (int)min((long long)T, in_len[b]);
+  const int NS = 2 * S + 1, NSmax = 2 * Smax + 1;
+  const long long* tg = targets + (long long)b * Smax;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    const long long tok = tg[j];
+    int f = j;
+    for (int i = 0; i < j; ++i)
+      if (tg[i] == tok) { f = i; break; }
+    first_occ[(long long)b * Smax + j] = (tok == blank) ? -1 : f;
+    if (f == j && tok != blank && tok >= 0 && tok < V) slot_of_class[(long long)b * V + tok] = (unsigned short)(j + 1);
+  }
+  if (threadIdx.x == 0 && blank >= 0 && blank < V) slot_of_class[(long long)b * V + blank] = 0;
+  float* cur = sh_ab + dir * 2 * (NSP + 2);
+  float* nxt = cur + (NSP + 2);
+  for (int i = threadIdx.x; i < 4 * (NSP + 2); i += blockDim.x) sh_ab[i] = NEG_INF;
+  __syncthreads();
+  const long long lp_stride = Smax + 1;
+  const float* lpb = lp + (long long)b * T * lp_stride;
+  float* outp = (dir == 0 ? alpha : beta) + (long long)b * T * NSmax;
+  const int off = dir == 0 ? 2 : 0;  // alpha reads s-1, s-2 through a 2-element guard; beta reads s+1, s+2 past the end
+  if (L > 0) {
+    const int tinit = dir == 0 ? 0 : L - 1;
+    for (int s = tid; s < NS; s += NTD) {
+      const int src = (s & 1) ? (s >> 1) + 1 : 0;
+      float v = NEG_INF;
+      if (dir == 0 ? (s <= 1) : (s >= NS - 2)) v = lpb[(long long)tinit * lp_stride + src];
+      outp[(long long)tinit * NSmax + s] = v;
+      cur[off + s] = v;
+    }
+    __syncthreads();
+    for (int step = 1; step < L; ++step) {
+      const int t = dir == 0 ? step : L - 1 - step;
+      for (int s = tid; s < NS; s += NTD) {
+        const int src = (s & 1) ? (s >> 1) + 1 : 0;
+        bool skip = false;
+        if (s & 1) {
+          if (dir == 0) skip = (s >= 3) && (tg[s >> 1] != tg[(s >> 1) - 1]);
+          else skip = (s + 2 < NS) && (tg[s >> 1] != tg[(s >> 1) + 1]);
+        }
+        float a0, a1, a2;
+        if (dir == 0) { a0 = cur[2 + s]; a1 = cur[2 + s - 1]; a2 = skip ? cur[2 + s - 2] : NEG_INF; }
+        else { a0 = cur[s]; a1 = (s + 1 < NS) ? cur[s + 1] : NEG_INF; a2 = skip ? cur[s + 2] : NEG_INF; }
+        const float nv = lse3(a0, a1, a2) + lpb[(long long)t * lp_stride + src];
+        outp[(long long)t * NSmax + s] = nv;
+        nxt[off + s] = nv;
+      }
+      __syncthreads();
+      float* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    if (dir == 0 && tid == 0) {
+      const float aL = cur[2 + NS - 1];
+      const float aL1 = NS >= 2 ? cur[2 + NS - 2] : NEG_INF;
+      const float nll = -lse2(aL, aL1);
+      nll_out[b] = nll;
+      if (nll != INFINITY) atomicAdd(loss, nll / (float)max(S, 1) / (float)B);
+    }
+  } else if (threadIdx.x == 0) {
+    nll_out[b] = (S == 0) ? 0.f : INFINITY;
+  }
+}
+
 template <typename TL, typename TG>
 __device__ __forceinline__ void store_grad(TG* p, long long i, float v);
 template <>
@@ -245,7 +322,8 @@ extern "C" int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int64_
                                      size_t workspace_bytes, tasr_stream_t stream) {
   if (B <= 0 || T <= 0 || V <= 0 || Smax < 0 || V > 65535 || ld < V) return TASR_ERR_SHAPE;
   const int NSP = nsp_for(Smax);
-  if (2 * NSP > 1024) return TASR_ERR_SHAPE;  // target length <= 255
+  const size_t ab_smem = (size_t)4 * (NSP + 2) * sizeof(float);
+  if (ab_smem > 200 * 1024) return TASR_ERR_SHAPE;  // targets beyond ~6000 labels per utterance
   if (workspace_bytes < tasr_ctc_workspace_bytes(B, T, V, Smax)) return TASR_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
@@ -273,11 +351,25 @@ extern "C" int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int64_
                                                           blank, lse, lp);
   TASR_CHECK_LAUNCH();
   float* nll_dst = nll != nullptr ? nll : nll_ws;
-  ctc_alpha_beta_kernel<<<B, 2 * NSP, (size_t)4 * (NSP + 2) * sizeof(float), st>>>(T, Smax, tg, il, tl, blank, V, lp, alpha,
-                                                                                 beta, nll_dst, loss, B, slots, first_occ);
+  if (2 * NSP <= 1024) {  // one thread per lattice state (targets up to 255 labels)
+    ctc_alpha_beta_kernel<<<B, 2 * NSP, ab_smem, st>>>(T, Smax, tg, il, tl, blank, V, lp, alpha, beta, nll_dst, loss, B, slots,
+                                                       first_occ);
+  } else {
+    if (ab_smem > 48 * 1024) {
+      cudaError_t ea = cudaFuncSetAttribute(ctc_alpha_beta_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab_smem);
+      if (ea != cudaSuccess) return tasr_set_cuda_error(ea);
+    }
+    ctc_alpha_beta_long_kernel<<<B, 1024, ab_smem, st>>>(T, Smax, tg, il, tl, blank, V, lp, alpha, beta, nll_dst, loss, B, slots,
+                                                         first_occ, NSP);
+  }
   TASR_CHECK_LAUNCH();
   if (dlogits != nullptr) {
     const size_t sm = (size_t)8 * (Smax + 1) * sizeof(float);
+    if (sm > 48 * 1024) {
+      cudaError_t eg = logits_bf16 ? cudaFuncSetAttribute(ctc_grad_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
+                                   : cudaFuncSetAttribute(ctc_grad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (eg != cudaSuccess) return tasr_set_cuda_error(eg);
+    }
     if (logits_bf16)
       ctc_grad_kernel<bf16><<<grid_rows, 256, sm, st>>>(reinterpret_cast<const bf16*>(logits), ld, B, T, V, Smax, il, tl, lse, lp,
                                                         alpha, beta, nll_dst, slots, first_occ, grad_scale,

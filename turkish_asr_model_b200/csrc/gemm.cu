@@ -191,6 +191,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int u = 0; u < 2; ++u) preload_aux_f32(p, row, n0 + sg * 64 + u * 32 + hsel * 16, res_first[u]);
       }
+      // The saved tensor of the NEXT tile of this CTA goes to L2 now: its loads (issued one tile later, when the
+      // accumulator is usually already waiting, so nothing hides them) then cost an L2 hit instead of an HBM round trip.
+      if ((HAS_AUX_BF16 || EPI == TASR_EPI_RESID) && !(p.flags & 1)) {
+        const int nt_ = tile + gridDim.x;
+        if (nt_ < total_tiles) {
+          const int nn0 = (nt_ % p.tiles_n) * TILE_N;
+          const int nrow = ((nt_ / p.tiles_n) % p.tiles_m) * BM + rloc;
+          if (nrow < p.M) {
+#pragma unroll 1
+            for (int g = sg; g < TILE_N / 64; g += 2) {
+              if (nn0 + g * 64 >= p.N) break;
+              if (EPI == TASR_EPI_RESID) {  // this thread: 2 x 16 fp32 (64 B each) at +0 and +32 columns
+                const float* a0 = reinterpret_cast<const float*>(p.aux) + (long long)nrow * p.ldaux + nn0 + g * 64 + hsel * 16;
+                prefetch_l2(a0);
+                prefetch_l2(a0 + 32);
+              } else {                      // 32 bf16 (64 B) of each half
+                const bf16* a0 = reinterpret_cast<const bf16*>(p.aux) + (long long)nrow * p.ldaux + nn0 + g * 64 + hsel * 32;
+                prefetch_l2(a0);
+                if (EPI != TASR_EPI_SILU_BWD) prefetch_l2(a0 + p.n_half);
+              }
+            }
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], aph);
       __syncwarp();
       tc_fence_after();
@@ -271,11 +295,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t lo_u[16], hi_u[16];
             tmem_ld16(tbase + coff, lo_u);
             if (DUAL) tmem_ld16(tbase + BN / 2 + coff, hi_u);
+            // rotary embedding: the partner columns (same head, other 32-column half) sit in this thread's TMEM lane
+            const bool rot = (EPI == TASR_EPI_ROPE) && (n0 + g * 64 < p.remap_p0);
+            if (EPI == TASR_EPI_ROPE && rot) tmem_ld16(tbase + g * 64 + (hsel ^ 1) * 32 + sub * 16, hi_u);
             tmem_ld_wait();
             float* lo = reinterpret_cast<float*>(lo_u);
             float* hi = reinterpret_cast<float*>(hi_u);
             float t3[16];
             if (HAS_AUX_BF16) epilogue_bwd16<EPI>(p, s32, row, col0, lo, hi, ax[sub]);
+            else if (EPI == TASR_EPI_ROPE) epilogue_rope16(p, row, col0, hsel, sub, rot, lo, hi);
             else epilogue_math<EPI, 16>(p, s32, row, col0, lo, hi, t3);
             if (sub == 0) {
               // the staging buffers are needed only now: the math above overlapped the TMA stores (their reads of
@@ -400,6 +428,12 @@ int fill_dev(const tasr_gemm_args* a, GemmDev* p, bool* dual) {
   p->seed_ptr = g_tasr_seed_ptr;
   p->remap_p0 = a->remap_p0; p->remap_p1 = a->remap_p1;
   p->colsum = (a->epilogue == TASR_EPI_ATOMIC) ? a->colsum : nullptr;
+  static int env_flags = -1;
+  if (env_flags < 0) {
+    const char* e = getenv("TASR_GEMM_FLAGS");
+    env_flags = e ? atoi(e) : 0;
+  }
+  p->flags = env_flags;
   if (a->colsum != nullptr && a->epilogue != TASR_EPI_ATOMIC) return TASR_ERR_SHAPE;
   const int num_kb = (a->K + BK - 1) / BK;
   int splits = (a->epilogue == TASR_EPI_ATOMIC && a->split_k > 1) ? a->split_k : 1;
@@ -519,6 +553,11 @@ extern "C" int tasr_gemm_bf16(const tasr_gemm_args* a, tasr_stream_t stream) {
     case TASR_EPI_RESID:
       if (!am && !bm) return launch_single<TASR_EPI_RESID, false, false>(a, p, st);
       break;
+    case TASR_EPI_ROPE:
+      if (am || bm || a->out_f32 || a->aux == nullptr || a->n_half <= 0 || a->remap_p0 <= 0 || (a->remap_p0 % 64) ||
+          a->remap_p0 > a->N || (reinterpret_cast<uintptr_t>(a->aux) & 15))
+        return TASR_ERR_SHAPE;
+      return launch_single<TASR_EPI_ROPE, false, false>(a, p, st);
     case TASR_EPI_SWIGLU:
       if (am || bm || (a->n_half % 64)) break;
       if (a->n_half % 128 == 0) return launch_tc<TASR_EPI_SWIGLU, 256, 2, 3, false, false>(a, p, st);

@@ -38,6 +38,7 @@ struct GemmDev {
   int remap_p0, remap_p1;
   int tiles_m, tiles_n;
   float* colsum;
+  int flags;  // experiment switches (TASR_GEMM_FLAGS in the environment); 0 in production
 };
 
 // W consecutive columns of one row (W = 16 or 32), vectorised when the chunk is full and 16-byte aligned
@@ -280,6 +281,30 @@ __device__ __forceinline__ void epilogue_math(const GemmDev& p, uint32_t s32, in
   } else if (EPI == TASR_EPI_ATOMIC) {
 #pragma unroll
     for (int i = 0; i < W; ++i) lo[i] *= p.alpha;
+  }
+}
+
+// Rotary position embedding on a 16-column piece of a 64-wide head (model/attention.py:62-70): with x1 = first half
+// and x2 = second half of the head, out1 = x1 cos - x2 sin, out2 = x2 cos + x1 sin.  `lo` = this thread's 16 columns
+// (accumulator), `pr` = the 16 partner columns 32 away in the same head (own TMEM lane, read by the caller);
+// hsel = which half `lo` is in; sub = which 16 of the 32 rotary indices.  Position = row % n_half (absolute frame index).
+__device__ __forceinline__ void epilogue_rope16(const GemmDev& p, int row, int col0, int hsel, int sub, bool rot, float* lo,
+                                                const float* pr) {
+  const int nvalid = (row < p.M) ? max(0, min(16, p.N - col0)) : 0;
+  float bb[16];
+  load_bias_w<16>(p.bias, col0, nvalid, bb);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) lo[i] += bb[i];
+  if (!rot) return;
+  load_bias_w<16>(p.bias, col0 + (hsel ? -32 : 32), 16, bb);  // rotated heads are always complete (remap_p0 % 64 == 0)
+  const int t = row % p.n_half;
+  const float4* cs = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + ((long long)t * 32 + sub * 16) * 2);
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float4 v = __ldg(cs + (i >> 1));  // (cos_i, sin_i, cos_i+1, sin_i+1)
+    const float p0 = pr[i] + bb[i], p1 = pr[i + 1] + bb[i + 1];
+    lo[i] = hsel ? fmaf(p0, v.y, lo[i] * v.x) : fmaf(-p0, v.y, lo[i] * v.x);
+    lo[i + 1] = hsel ? fmaf(p1, v.w, lo[i + 1] * v.z) : fmaf(-p1, v.w, lo[i + 1] * v.z);
   }
 }
 

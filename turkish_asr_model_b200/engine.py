@@ -308,8 +308,9 @@ class ConformerEngine:
         qkv = torch.empty(M, d + 2 * DH, dtype=torch.bfloat16, device=dev)
         wqkv = S(pre + "attn.linear_q.weight", self.qkv_w_shape)
         bqkv = P(pre + "attn.linear_q.bias", (d + 2 * DH,))
-        L.gemm(M, d + 2 * DH, d, xn2.view(M, d), d, wqkv, d, L.EPI_STORE, qkv, d + 2 * DH, bias=bqkv)
-        L.rope_inplace(qkv, T, d + DH, cs)
+        # fused q|k|v projection; RoPE (model/attention.py:228-230) is applied to the q and k heads in the epilogue
+        L.gemm(M, d + 2 * DH, d, xn2.view(M, d), d, wqkv, d, L.EPI_ROPE, qkv, d + 2 * DH, bias=bqkv, aux=cs, n_half=T,
+               remap_p0=d + DH)
         ctx, lse2 = L.mqa_fwd(qkv, B, T, H, d, key_len, drop_p=drop, seed=seed + 2)
         x2 = torch.empty(M, d, dtype=torch.float32, device=dev)
         L.gemm(M, d, d, ctx, d, S(pre + "attn.linear_out.weight"), d, L.EPI_RESID, x2, d,

@@ -191,8 +191,7 @@ class _AttentionFn(torch.autograd.Function):
         bqkv = torch.cat([bq.detach(), bk.detach(), bv.detach()], 0).float().contiguous()
         nq = d + 2 * DH
         qkv = torch.empty(M, nq, dtype=torch.bfloat16, device=x.device)
-        L.gemm(M, nq, d, xb, d, wqkv, d, L.EPI_STORE, qkv, nq, bias=bqkv)
-        L.rope_inplace(qkv, T, d + DH, cs)
+        L.gemm(M, nq, d, xb, d, wqkv, d, L.EPI_ROPE, qkv, nq, bias=bqkv, aux=cs, n_half=T, remap_p0=d + DH)
         c, lse2 = L.mqa_fwd(qkv, B, T, H, d, key_len, drop_p=drop, seed=seed)
         wob = _bf(wo)
         res = _f32(residual).view(M, d) if residual is not None else torch.zeros(M, d, dtype=torch.float32, device=x.device)
