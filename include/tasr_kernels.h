@@ -250,8 +250,11 @@ int tasr_specaugment(float* feats, int B, int T, int F, const int32_t* params, i
  * Replaces: trainer/trainer.py:167-173 (log_softmax + nn.CTCLoss(blank=0, zero_infinity=True)) and
  *   their backward.  logits (B,T,V) bf16 or fp32 with row pitch ld >= V elements (dlogits: same pitch); targets (B,Smax) int64 padded; lengths int64 (B),
  *   all on the device.  loss (1) fp32 = mean_b(nll_b / max(S_b,1)), infeasible samples contribute 0;
- *   nll (B) fp32 or NULL; dlogits same dtype/shape as logits (or NULL) =
+ *   nll (B) fp32 or NULL; dlogits (or NULL), same shape and row pitch as the logits =
  *   grad_scale * (softmax - occupancy) / (B * max(S_b,1)) for t < input_lengths[b], else 0.
+ *   logits_bf16: 0 = fp32 logits and gradient, 1 = bf16 logits and gradient (the training path: the gradient is the
+ *   bf16 operand of the classifier's backward GEMMs), 2 = bf16 logits, fp32 gradient (the arithmetic is fp32 in all
+ *   three; 2 exposes it unrounded).
  * ---------------------------------------------------------------------------------------------- */
 size_t tasr_ctc_workspace_bytes(int B, int T, int V, int Smax);
 int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int64_t ld, int B, int T, int V, const int64_t* targets, int Smax,

@@ -414,8 +414,10 @@ def _rows_view(logits):
     return logits, V
 
 
-def ctc_loss_fwd_bwd(logits, targets, input_lengths, target_lengths, blank=0, grad_scale=1.0, want_grad=True):
-    """logits (B,T,V) bf16|fp32; targets (B,Smax) int64; lengths int64 (device) -> (loss (1), nll (B), dlogits)."""
+def ctc_loss_fwd_bwd(logits, targets, input_lengths, target_lengths, blank=0, grad_scale=1.0, want_grad=True,
+                     grad_dtype=None):
+    """logits (B,T,V) bf16|fp32; targets (B,Smax) int64; lengths int64 (device) -> (loss (1), nll (B), dlogits).
+    grad_dtype=torch.float32 with bf16 logits returns the gradient unrounded (default: the logits' dtype)."""
     require_cuda(logits, targets, input_lengths, target_lengths)
     B, T, V = logits.shape
     logits, ld = _rows_view(logits)
@@ -423,13 +425,19 @@ def ctc_loss_fwd_bwd(logits, targets, input_lengths, target_lengths, blank=0, gr
     loss = torch.empty(1, dtype=torch.float32, device=logits.device)
     nll = torch.empty(B, dtype=torch.float32, device=logits.device)
     dlogits = None
+    mode = int(logits.dtype == torch.bfloat16)
     if want_grad:  # same row pitch as the logits; padding columns (if any) are zero
-        dl = torch.zeros(B * T, ld, dtype=logits.dtype, device=logits.device) if ld != V else \
-            torch.empty(B * T, ld, dtype=logits.dtype, device=logits.device)
+        gdt = logits.dtype if grad_dtype is None else grad_dtype
+        if gdt != logits.dtype:
+            if not (logits.dtype == torch.bfloat16 and gdt == torch.float32):
+                raise TasrError("grad_dtype: only an fp32 gradient for bf16 logits differs from the logits dtype")
+            mode = 2
+        dl = torch.zeros(B * T, ld, dtype=gdt, device=logits.device) if ld != V else \
+            torch.empty(B * T, ld, dtype=gdt, device=logits.device)
         dlogits = dl.view(B, T, ld)[:, :, :V]
     wsb = lib().tasr_ctc_workspace_bytes(B, T, V, Smax)
     ws = workspace(wsb, logits.device)
-    check(lib().tasr_ctc_loss_fwd_bwd(ptr(logits), int(logits.dtype == torch.bfloat16), ld, B, T, V, ptr(targets), Smax,
+    check(lib().tasr_ctc_loss_fwd_bwd(ptr(logits), mode, ld, B, T, V, ptr(targets), Smax,
                                       ptr(input_lengths), ptr(target_lengths), blank, grad_scale, ptr(loss), ptr(nll),
                                       ptr(dlogits), ptr(ws), wsb, stream_ptr()))
     return loss, nll, dlogits

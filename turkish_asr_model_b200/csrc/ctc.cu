@@ -234,14 +234,12 @@ __global__ void __launch_bounds__(1024) ctc_alpha_beta_long_kernel(int T, int Sm
   }
 }
 
-template <typename TL, typename TG>
-__device__ __forceinline__ void store_grad(TG* p, long long i, float v);
-template <>
-__device__ __forceinline__ void store_grad<float, float>(float* p, long long i, float v) { p[i] = v; }
-template <>
-__device__ __forceinline__ void store_grad<bf16, bf16>(bf16* p, long long i, float v) { p[i] = __float2bfloat16(v); }
+__device__ __forceinline__ void store_grad(float* p, long long i, float v) { p[i] = v; }
+__device__ __forceinline__ void store_grad(bf16* p, long long i, float v) { p[i] = __float2bfloat16(v); }
 
-template <typename TL>
+// TL = logits dtype, TG = gradient dtype (bf16 logits may ask for an fp32 gradient: the arithmetic is fp32 either way,
+// bf16 is only the storage format the classifier's backward GEMMs consume)
+template <typename TL, typename TG>
 __global__ void __launch_bounds__(256) ctc_grad_kernel(const TL* __restrict__ logits, long long ld, int B, int T, int V, int Smax,
                                                        const long long* __restrict__ in_len,
                                                        const long long* __restrict__ tgt_len,
@@ -250,7 +248,7 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const TL* __restrict__ lo
                                                        const float* __restrict__ nll_in,
                                                        const unsigned short* __restrict__ slot_of_class,
                                                        const int* __restrict__ first_occ, float grad_scale,
-                                                       TL* __restrict__ dlogits) {
+                                                       TG* __restrict__ dlogits, long long ldg) {
   extern __shared__ float sh_gam[];  // per warp: Smax + 1 occupancies
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -259,12 +257,12 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const TL* __restrict__ lo
   const int L = (int)min((long long)T, in_len[b]);
   const int S = (int)tgt_len[b];
   const float nll = nll_in[b];
-  TL* drow = dlogits + ((long long)b * T + t) * ld;
+  TG* drow = dlogits + ((long long)b * T + t) * ldg;
   if (t >= L || nll == INFINITY || nll != nll) {
     // padding frames and infeasible samples: exactly 0 (zero_infinity); a NaN sample poisons its rows so that the
     // non-finite gradient norm makes the optimizer skip the step (reference trainer/trainer.py:178-181)
     const float fill = (nll != nll && t < L) ? nll : 0.f;
-    for (int c = lane; c < V; c += 32) store_grad<TL, TL>(drow, c, fill);
+    for (int c = lane; c < V; c += 32) store_grad(drow, c, fill);
     return;
   }
   float* gam = sh_gam + wib * (Smax + 1);
@@ -295,7 +293,7 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const TL* __restrict__ lo
     float v = expf(ldlogit(row, c) - lse);
     const unsigned short sl = slots[c];
     if (sl != 0xFFFF) v -= gam[sl];
-    store_grad<TL, TL>(drow, c, v * scale);
+    store_grad(drow, c, v * scale);
   }
 }
 
@@ -365,19 +363,23 @@ extern "C" int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int64_
   TASR_CHECK_LAUNCH();
   if (dlogits != nullptr) {
     const size_t sm = (size_t)8 * (Smax + 1) * sizeof(float);
-    if (sm > 48 * 1024) {
-      cudaError_t eg = logits_bf16 ? cudaFuncSetAttribute(ctc_grad_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
-                                   : cudaFuncSetAttribute(ctc_grad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      if (eg != cudaSuccess) return tasr_set_cuda_error(eg);
-    }
-    if (logits_bf16)
-      ctc_grad_kernel<bf16><<<grid_rows, 256, sm, st>>>(reinterpret_cast<const bf16*>(logits), ld, B, T, V, Smax, il, tl, lse, lp,
-                                                        alpha, beta, nll_dst, slots, first_occ, grad_scale,
-                                                        reinterpret_cast<bf16*>(dlogits));
+    auto launch_grad = [&](auto kern, auto* lg, auto* dg) -> cudaError_t {
+      if (sm > 48 * 1024) {
+        cudaError_t eg = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (eg != cudaSuccess) return eg;
+      }
+      kern<<<grid_rows, 256, sm, st>>>(lg, ld, B, T, V, Smax, il, tl, lse, lp, alpha, beta, nll_dst, slots, first_occ, grad_scale,
+                                       dg, ld);
+      return cudaSuccess;
+    };
+    cudaError_t eg;
+    if (logits_bf16 == 1)
+      eg = launch_grad(ctc_grad_kernel<bf16, bf16>, reinterpret_cast<const bf16*>(logits), reinterpret_cast<bf16*>(dlogits));
+    else if (logits_bf16 == 2)
+      eg = launch_grad(ctc_grad_kernel<bf16, float>, reinterpret_cast<const bf16*>(logits), reinterpret_cast<float*>(dlogits));
     else
-      ctc_grad_kernel<float><<<grid_rows, 256, sm, st>>>(reinterpret_cast<const float*>(logits), ld, B, T, V, Smax, il, tl, lse,
-                                                         lp, alpha, beta, nll_dst, slots, first_occ, grad_scale,
-                                                         reinterpret_cast<float*>(dlogits));
+      eg = launch_grad(ctc_grad_kernel<float, float>, reinterpret_cast<const float*>(logits), reinterpret_cast<float*>(dlogits));
+    if (eg != cudaSuccess) return tasr_set_cuda_error(eg);
     TASR_CHECK_LAUNCH();
   }
   return TASR_OK;
