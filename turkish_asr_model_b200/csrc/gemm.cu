@@ -499,7 +499,8 @@ int launch_tc(const tasr_gemm_args* a, GemmDev& p, cudaStream_t st) {
   // of 148 with 2-3; the makespan is the same and the other SMs stay free for the kernels of the second stream
   const int num_sms = tasr_num_sms();
   const long long rounds = (total + num_sms - 1) / num_sms;
-  const int grid = (int)((total + rounds - 1) / rounds);
+  int grid = (int)((total + rounds - 1) / rounds);
+  if (p.flags & 2) grid = (int)(total < num_sms ? total : num_sms);  // experiment: every SM takes tiles
   cudaError_t lerr = launch_pdl(kern, dim3(grid), dim3(G_THREADS), (size_t)SMEM, st, tmA, tmB, tmO, tmO2, p);
   if (lerr != cudaSuccess) return tasr_set_cuda_error(lerr);
   TASR_CHECK_LAUNCH();
