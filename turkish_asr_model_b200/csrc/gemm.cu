@@ -525,6 +525,15 @@ int launch_single(const tasr_gemm_args* a, GemmDev& p, cudaStream_t st) {
   // per epilogue group buys one more operand stage (deeper TMA look-ahead)
   constexpr bool LONGK = (EPI == TASR_EPI_ATOMIC);
   constexpr int R = LONGK ? 1 : 2;
+  if (LONGK && (p.flags & 12)) {  // experiment: smaller shared-memory footprint for the weight-gradient kernels, so that
+                                  // their CTAs can share an SM with the small-footprint kernels of the main chain
+    if (p.flags & 4) {
+      if (use_wide(a->M, a->N, p.splits)) return launch_tc<EPI, 256, LONGK ? 3 : 3, R, A_MN, B_MN>(a, p, st);
+      return launch_tc<EPI, 128, LONGK ? 4 : 4, R, A_MN, B_MN>(a, p, st);
+    }
+    if (use_wide(a->M, a->N, p.splits)) return launch_tc<EPI, 256, LONGK ? 2 : 3, R, A_MN, B_MN>(a, p, st);
+    return launch_tc<EPI, 128, LONGK ? 3 : 4, R, A_MN, B_MN>(a, p, st);
+  }
   if (use_wide(a->M, a->N, p.splits)) return launch_tc<EPI, 256, LONGK ? 4 : 3, R, A_MN, B_MN>(a, p, st);
   return launch_tc<EPI, 128, LONGK ? 6 : 4, R, A_MN, B_MN>(a, p, st);
 }
