@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from turkish_asr_model_b200 import _lib as L
 
 dev = torch.device("cuda:0")
-M, d, dff = 21248, 256, 1024
+M, d, dff = 21248, int(os.environ.get("PG_D", "256")), int(os.environ.get("PG_DFF", "1024"))
 g = torch.Generator(device=dev).manual_seed(0)
 def rb(*s): return (torch.randn(*s, generator=g, device=dev) * 0.5).to(torch.bfloat16)
 x = rb(M, d); W1 = rb(2 * dff, d); b1 = torch.randn(2 * dff, device=dev)
