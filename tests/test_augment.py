@@ -106,3 +106,11 @@ def test_batched_inference_ids(cuda):
     ids = inf.transcribe_ids(waves.to(cuda), ns)
     _, ref_ids = oc.greedy_ids(logits.float().cpu(), lengths)
     assert ids == ref_ids
+    # staged host batches (copy stream + reusable device buffers) give the same ids; handles can be prepared ahead
+    hw = waves.pin_memory()
+    h0, h1 = inf.stage(hw), inf.stage(hw)
+    assert inf.transcribe_ids(h0, ns) == ref_ids and inf.transcribe_ids(h1, ns) == ref_ids
+    h2 = inf.stage(hw)
+    assert inf.transcribe_ids(h2, ns) == ref_ids and len(inf._staged) <= 3
+    jobs = [inf.submit(inf.stage(hw), ns) for _ in range(2)]  # asynchronous form: results are read later
+    assert [j.result() for j in jobs] == [ref_ids, ref_ids]
