@@ -351,3 +351,46 @@ def test_autograd_path_sees_torch_optimizer_updates(cuda):
         model.fc.weight.data.mul_(2.0)
         model.fc.bias.data.mul_(2.0)
     assert rel(model(x.to(cuda), il), 2.0 * ref_old) < 2e-2
+
+
+# ------------------------------------------------------------------ the reference's outer loop
+def test_fit_validate_checkpoint_and_resume(cuda, tmp_path):
+    """Trainer.fit() as main.py drives it (reference trainer/trainer.py:284-319): epochs over a loader of collated
+    batches, validation each epoch, periodic + best + final checkpoints, then a second Trainer with resume=True picks up
+    at the next epoch with the same weights and optimizer state."""
+    from turkish_asr_model_b200.data.dataset import collate_fn
+    torch.manual_seed(21)
+    model = TurkishASRModel(80, 256, 4, 1, 40, dropout=0.0).to(cuda)
+    g = torch.Generator().manual_seed(22)
+    items = [(torch.randn(70 + 9 * i, 80, generator=g), torch.randint(1, 40, (4 + i % 3,), generator=g)) for i in range(8)]
+    train = [collate_fn(items[i: i + 2]) for i in range(0, 8, 2)] + [(None, None, None, None)]  # a failed batch is skipped
+    valid = [collate_fn(items[:3])]
+
+    class C(Cfg):
+        epochs = 2
+        save_interval = 1
+        output_model_path = "final_model.pt"
+    cfg = C()
+    cfg.checkpoint_dir = str(tmp_path)
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=1e-6)
+    tr = Trainer(model, train, opt, _sched(opt), cuda, cfg, None, valid_loader=valid, gradient_clip=1.0)
+    v0 = tr.validate(0)
+    tr.fit()
+    v2 = tr.validate(2)
+    assert np.isfinite(v0) and np.isfinite(v2) and v2 < v0          # two epochs of training lowered the validation loss
+    assert tr.global_step == 8 and tr.scheduler.last_epoch == 8
+    for name in ("checkpoint_epoch_1.pt", "checkpoint_epoch_2.pt", "best_model.pt", "final_model.pt"):
+        assert os.path.exists(os.path.join(tmp_path, name)), name
+    assert tr.best_val_loss <= v2 + 1e-6 and tr.best_val_loss < v0  # best over the epochs (epoch 1 may beat epoch 2)
+
+    torch.manual_seed(99)
+    model2 = TurkishASRModel(80, 256, 4, 1, 40, dropout=0.0).to(cuda)
+    cfg2 = C()
+    cfg2.checkpoint_dir, cfg2.resume, cfg2.epochs = str(tmp_path), True, 3
+    opt2 = torch.optim.AdamW(model2.parameters(), lr=5e-4, weight_decay=1e-6)
+    tr2 = Trainer(model2, train, opt2, _sched(opt2), cuda, cfg2, None, valid_loader=valid, gradient_clip=1.0)
+    tr2.load_checkpoint()
+    assert tr2.start_epoch == 3 and tr2.global_step == 8 and tr2._opt_step == 8
+    assert abs(tr2.validate(2) - v2) < 1e-4 * abs(v2)                # same weights and BatchNorm buffers
+    tr2.fit()                                                        # runs epoch 3 only
+    assert tr2.global_step == 12
