@@ -1,8 +1,9 @@
 # A/B of experiment switches: TASR_GEMM_FLAGS bits (1 = no L2 prefetch of the next tile's saved tensor, 2 = GEMM grids use
 # every SM instead of ceil(tiles / rounds) CTAs, 4 / 8 = weight-gradient kernels with 3 / 2 operand stages),
-# TASR_NO_WGRAD_OVERLAP=1 (weight gradients on the main stream)
+# TASR_NO_WGRAD_OVERLAP=1 (weight gradients on the main stream).  Run-to-run noise of the step time is about +-0.5 %:
+# repeat every setting (AB_REPS, default 3).
 run() { env "$@" python bench.py --steps 20 --warmup 5 --no-cpu 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$*', round(d['value']), round(d['ms_per_step'],3), round(d['roofline']['step_ms_this_batch'],3), round(d['roofline']['gemm_ms_per_step'],3))
 "; }
-for i in 1 2; do for f in ${AB_FLAGS:-0 4 8}; do run TASR_GEMM_FLAGS=$f; done; done
+for i in $(seq ${AB_REPS:-3}); do for f in ${AB_FLAGS:-0 4}; do run TASR_GEMM_FLAGS=$f; done; done

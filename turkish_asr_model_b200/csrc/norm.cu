@@ -648,9 +648,9 @@ extern "C" int tasr_groupnorm_bwd(const void* dy, int dy_bf16, const float* x, i
   if (workspace_bytes < tasr_groupnorm_workspace_bytes(B, T, d)) return TASR_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if ((long long)T * d * sizeof(float) <= GN_FUSED_MAX_SLICE) {
-    // 2 CTAs per SM: stand-alone the kernel is ~25 % faster with 4 (more loads in flight), but inside the training step
-    // the extra resident CTAs displace the weight-gradient kernels of the side stream and the step gets slower (measured)
-    const int cl = gn_cluster_size(B, T, 2);
+    // up to 4 CTAs per SM (64 registers): 24 % faster than 2 per SM stand-alone on cold operands (more loads in flight);
+    // inside the training step, where the kernel shares the memory system with the weight-gradient stream, +0.3 %
+    const int cl = gn_cluster_size(B, T, 4);
     const int frows = cdiv(T, cl);
     const size_t fsm = ((size_t)4 * d + 2 * G) * sizeof(float);
     const unsigned long long seed64 = cast_seed;
