@@ -157,7 +157,9 @@ int tasr_groupnorm_bwd(const void* dy, int dy_bf16, const float* x, int B, int T
  *   weight (d, 31) fp32 == the reference (d,1,31) tensor; bn_partial (tasr_dwconv_bn_parts, d, 2) fp32.
  *   bn stats (d, 2) fp32 = (mean, rstd).
  *   dwconv bwd: dw (M,d) bf16 in; ab (M,2d) saved GLU input (may be NULL -> du written to `du`);
- *   dab (M,2d) bf16 out; dweight (d,31), dbias (d) accumulated (+=).
+ *   dab (M,2d) bf16 out; dweight (d,31), dbias (d) accumulated (+=).  The two halves are independent kernels:
+ *   dab == du == NULL runs only the weight/bias-gradient kernel, dweight == NULL only the data kernel (so that a
+ *   caller can put the weight half, a leaf of the backward graph, on another stream).
  * ---------------------------------------------------------------------------------------------- */
 int tasr_dwconv_bn_parts(int B, int T);
 int tasr_dwconv31_fwd(const void* u, int B, int T, int d, const float* weight, const float* bias, void* out,

@@ -273,6 +273,21 @@ def dwconv_bwd(dw, u, ab, weight, dweight, dbias):
     return dab if ab is not None else du
 
 
+def dwconv_bwd_data(dw, u, ab, weight):
+    """Data half of dwconv_bwd: returns d(a|b) (GLU backward fused) or du when ab is None."""
+    B, T, d = u.shape
+    dab = torch.empty(B, T, 2 * d, dtype=torch.bfloat16, device=u.device) if ab is not None else None
+    du = torch.empty_like(u) if ab is None else None
+    check(lib().tasr_dwconv31_bwd(ptr(dw), ptr(u), ptr(ab), B, T, d, ptr(weight), ptr(dab), ptr(du), None, None, stream_ptr()))
+    return dab if ab is not None else du
+
+
+def dwconv_bwd_weight(dw, u, weight, dweight, dbias):
+    """Weight / bias-gradient half of dwconv_bwd (accumulates): a leaf of the backward graph."""
+    B, T, d = u.shape
+    check(lib().tasr_dwconv31_bwd(ptr(dw), ptr(u), None, B, T, d, ptr(weight), None, None, ptr(dweight), ptr(dbias), stream_ptr()))
+
+
 def bn_finalize(part, d, count, eps, momentum, training, running_mean, running_var, num_batches_tracked):
     stats = torch.empty(d, 2, dtype=torch.float32, device=running_mean.device)
     npart = part.shape[0] if part is not None else 0

@@ -294,9 +294,12 @@ extern "C" int tasr_dwconv31_bwd(const void* dw, const void* u, const void* ab, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int ntiles = cdiv(T, TT);
   dim3 grid_a(d / CC, ntiles, B);
-  dwconv_bwd_data_kernel<<<grid_a, DW_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dw), reinterpret_cast<const bf16*>(ab), T, d,
-                                                        weight, reinterpret_cast<bf16*>(dab), reinterpret_cast<bf16*>(du));
-  TASR_CHECK_LAUNCH();
+  if (dab != nullptr || du != nullptr) {  // data half (main chain)
+    dwconv_bwd_data_kernel<<<grid_a, DW_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dw), reinterpret_cast<const bf16*>(ab), T,
+                                                          d, weight, reinterpret_cast<bf16*>(dab), reinterpret_cast<bf16*>(du));
+    TASR_CHECK_LAUNCH();
+  }
+  if (dweight == nullptr) return TASR_OK;  // weight half is a leaf of the backward graph: callers may run it elsewhere
   int nseg = 1184 / max(1, B * (d / CC));  // up to ~8 CTAs per SM of work, otherwise as few segments (= atomics) as possible
   nseg = max(1, min(nseg, ntiles));
   const int tiles_per_cta = cdiv(ntiles, nseg);

@@ -531,9 +531,11 @@ class ConformerEngine:
         L.gemm(M, d, d, dy, d, S(pre + "conv.pointwise_conv2.weight", (d, d)), d, L.EPI_STORE, ds, d, b_mn=1)
         dw = L.bn_silu_bwd(ds, sv["w"], sv["bnst"], P(pre + "conv.batch_norm.weight"), P(pre + "conv.batch_norm.bias"),
                            Gv(pre + "conv.batch_norm.weight"), Gv(pre + "conv.batch_norm.bias"))
-        dab = L.dwconv_bwd(dw.view(B, T, d), sv["u"].view(B, T, d), sv["ab"].view(B, T, 2 * d),
-                           P(pre + "conv.depthwise_conv.weight", (d, 31)), Gv(pre + "conv.depthwise_conv.weight", (d, 31)),
-                           Gv(pre + "conv.depthwise_conv.bias")).view(M, 2 * d)
+        # the 31-tap weight / bias gradient is a leaf: side stream; the data half (with the GLU backward) stays on the chain
+        dwv, uv, wdw = dw.view(B, T, d), sv["u"].view(B, T, d), P(pre + "conv.depthwise_conv.weight", (d, 31))
+        self._leaf(lambda: L.dwconv_bwd_weight(dwv, uv, wdw, Gv(pre + "conv.depthwise_conv.weight", (d, 31)),
+                                               Gv(pre + "conv.depthwise_conv.bias")), dw)
+        dab = L.dwconv_bwd_data(dwv, uv, sv["ab"].view(B, T, 2 * d), wdw).view(M, 2 * d)
         self._wgrad_bias(dab, sv["xn3"].view(M, d), 2 * d, d, M, Gv(pre + "conv.pointwise_conv1.weight", (2 * d, d)),
                          Gv(pre + "conv.pointwise_conv1.bias"))
         dxn = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
