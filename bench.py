@@ -341,11 +341,19 @@ def kernel_rooflines(model, batch, dev, peaks, traffic):
     fl = 2.0 * (M * F2) * d * 9 * d
     entry("conv2_fwd", "tensor", fl, _timed(lambda: L.conv2_fwd(y1, T, 80, w2p, P("subsample.2.bias")), 5, flush))
     z2, y2 = L.conv2_fwd(y1, T, 80, w2p, P("subsample.2.bias"))
+    entry("conv1_fwd", "hbm", float(feats.numel()) * 4 + float(y1.numel()) * 2,
+          _timed(lambda: L.conv1_fwd(feats, P("subsample.0.weight"), P("subsample.0.bias")), 5, flush),
+          "K = 9 convolution on tcgen05 (in-kernel im2col, split-bf16 operands) + SiLU; bytes = features in + NHWC bf16 out")
     dz2 = (0.01 * torch.randn(M * F2, d, device=dev, generator=g)).to(torch.bfloat16)
     entry("conv2_dgrad", "tensor", fl, _timed(lambda: L.conv2_dgrad(dz2, B, T, 80, w2p), 5, flush))
     gw2 = torch.zeros(d, d, 3, 3, device=dev)
     entry("conv2_wgrad", "tensor", fl, _timed(lambda: L.conv2_wgrad(dz2, y1, T, 80, gw2), 5, flush))
-    del y1, z2, y2, dz2
+    dy1 = L.conv2_dgrad(dz2, B, T, 80, w2p)
+    gw1, gb1 = torch.zeros(d, 1, 3, 3, device=dev), torch.zeros(d, device=dev)
+    entry("conv1_bwd", "hbm", float(feats.numel()) * 4 + float(dy1.numel()) * 2,
+          _timed(lambda: L.conv1_bwd(dy1, feats, P("subsample.0.weight"), P("subsample.0.bias"), gw1, gb1), 5, flush),
+          "recomputes the pre-activation, dW1 / db1 accumulated in TMEM; bytes = features + NHWC bf16 gradient in")
+    del y1, z2, y2, dz2, dy1
     # ---- GroupNorm
     x = torch.randn(B, T2, d, device=dev, generator=g)
     gam, bet = P("blocks.0.norm_ff1.norm.weight"), P("blocks.0.norm_ff1.norm.bias")
@@ -379,6 +387,21 @@ def kernel_rooflines(model, batch, dev, peaks, traffic):
     entry("mqa_attention_bwd", "tensor", 2.5 * att_fl,
           _timed(lambda: L.mqa_bwd(qkv, ctx, dctx, lse2, B, T2, H, d, key_len, cs, drop_p=0.1, seed=1), 5, flush),
           "delta + persistent backward + finalize (incl. inverse RoPE)")
+    # ---- optimizer
+    n_live = flat.live_numel
+    pbuf, gbuf = flat.params[:n_live].clone(), torch.randn(n_live, device=dev, generator=g) * 1e-3
+    mbuf, vbuf = torch.zeros(n_live, device=dev), torch.zeros(n_live, device=dev)
+    sh = torch.empty(n_live, dtype=torch.bfloat16, device=dev)
+    hyper = torch.tensor([5e-4, 0.9, 0.999, 1e-8, 1e-6, 0.1, 0.001, 1.0, 1.0], device=dev)
+    ssq, nrm = torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros(1, device=dev)
+
+    def opt_step():
+        ssq.zero_()
+        L.grad_sumsq(gbuf, ssq)
+        L.clip_adamw(pbuf, gbuf, mbuf, vbuf, sh, hyper, ssq, nrm)
+    entry("clip_adamw", "hbm", float(n_live) * (4 + 4 + 4 + 8 + 8 + 2), _timed(opt_step, 5, flush),
+          "gradient sum of squares + clip + AdamW + bf16 operand refresh: grad read twice, param / moments read+write, shadow write")
+    del pbuf, gbuf, mbuf, vbuf, sh
     # ---- CTC
     Vp = (V + 7) // 8 * 8
     logits = (torch.randn(B, T2, Vp, device=dev, generator=g)).to(torch.bfloat16)[:, :, :V]

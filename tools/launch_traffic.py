@@ -75,6 +75,9 @@ if '--json' in sys.argv:
         'mqa_attention_fwd': per_call(lambda k: k.startswith('mqa_fwd'), n_blk),
         'mqa_attention_bwd': per_call(lambda k: k.startswith(('mqa_bwd', 'attn_delta', 'attn_dq_finalize')), n_blk),
         'ctc_loss_fwd_bwd': per_call(lambda k: k.startswith('ctc_'), 1),
+        'conv1_fwd': per_call(lambda k: k.startswith(('conv1_tc_fwd', 'conv1_fwd')), 1),
+        'conv1_bwd': per_call(lambda k: k.startswith(('conv1_tc_bwd', 'conv1_bwd')), 1),
+        'clip_adamw': per_call(lambda k: k.startswith(('sumsq_kernel', 'adamw_kernel')), 1),
     }
     json.dump(out, open(sys.argv[sys.argv.index('--json') + 1], 'w'), indent=1)
     print('wrote', sys.argv[sys.argv.index('--json') + 1])
