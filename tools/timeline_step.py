@@ -65,25 +65,26 @@ main = max(streams, key=lambda s: sum(e["dur"] for e in streams[s]))
 for s, lst in sorted(streams.items(), key=lambda kv: -sum(e["dur"] for e in kv[1])):
     print("  stream %s: %d activities/step, busy %.1f us/step%s" % (s, len(lst) // NSTEP, sum(e["dur"] for e in lst) / NSTEP,
                                                                    "  <- main chain" if s == main else ""))
-lst = streams[main]
-gaps = collections.defaultdict(lambda: [0, 0.0])
-tot_gap, n_gap, hist = 0.0, 0, collections.Counter()
-for a, b2 in zip(lst[:-1], lst[1:]):
-    g = b2["ts"] - (a["ts"] + a["dur"])
-    if g > 200:  # boundary between two steps (host side)
-        continue
-    g = max(g, 0.0)
-    tot_gap += g
-    n_gap += 1
-    hist[min(int(g), 10)] += 1
-    key = short(a["name"]) + "  ->  " + short(b2["name"])
-    gaps[key][0] += 1
-    gaps[key][1] += g
-print("main chain: idle between consecutive kernels %.1f us/step over %d boundaries/step (mean %.2f us)" % (
-    tot_gap / NSTEP, n_gap // NSTEP, tot_gap / max(n_gap, 1)))
-print("gap histogram (us -> count/step):", {k: v // NSTEP for k, v in sorted(hist.items())})
-for k, (n, t) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
-    print("%9.1f us/step  n=%3d  mean %5.2f  %s" % (t / NSTEP, n // NSTEP, t / n, k))
+for sid in [s for s in streams if len(streams[s]) // NSTEP >= 20]:
+    lst = streams[sid]
+    gaps = collections.defaultdict(lambda: [0, 0.0])
+    tot_gap, n_gap, hist = 0.0, 0, collections.Counter()
+    for a, b2 in zip(lst[:-1], lst[1:]):
+        g = b2["ts"] - (a["ts"] + a["dur"])
+        if g > 2000:  # boundary between two steps (host side)
+            continue
+        g = max(g, 0.0)
+        tot_gap += g
+        n_gap += 1
+        hist[min(int(g), 10)] += 1
+        key = short(a["name"]) + "  ->  " + short(b2["name"])
+        gaps[key][0] += 1
+        gaps[key][1] += g
+    print("stream %s: idle between consecutive kernels %.1f us/step over %d boundaries/step (mean %.2f us)" % (
+        sid, tot_gap / NSTEP, n_gap // NSTEP, tot_gap / max(n_gap, 1)))
+    print("  gap histogram (us -> count/step):", {k: v // NSTEP for k, v in sorted(hist.items())})
+    for k, (n, t) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:14]:
+        print("  %9.1f us/step  n=%3d  mean %6.2f  %s" % (t / NSTEP, n // NSTEP, t / n, k))
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in ev:
     agg[short(e["name"])][0] += 1
