@@ -1,5 +1,6 @@
 # A/B of experiment switches: TASR_GEMM_FLAGS bits (1 = no L2 prefetch of the next tile's saved tensor, 2 = GEMM grids use
-# every SM instead of ceil(tiles / rounds) CTAs, 4 / 8 = weight-gradient kernels with 3 / 2 operand stages),
+# every SM instead of ceil(tiles / rounds) CTAs, 4 = weight-gradient kernels with the deep 4 / 6-stage ring, 32 = narrow
+# weight-gradient tiles with 3 stages, 64 = 128-wide tiles for the K >= 2048 dgrad),
 # TASR_NO_WGRAD_OVERLAP=1 (weight gradients on the main stream).  Run-to-run noise of the step time is about +-0.5 %:
 # repeat every setting (AB_REPS, default 3).
 run() { env "$@" python bench.py --steps 20 --warmup 5 --no-cpu 2>/dev/null | python -c "
