@@ -567,7 +567,12 @@ extern "C" int tasr_gemm_bf16(const tasr_gemm_args* a, tasr_stream_t stream) {
       if (am && bm) return launch_single<TASR_EPI_STORE, true, true>(a, p, st);
       return launch_tc<TASR_EPI_STORE, 128, 4, 2, true, false>(a, p, st);
     case TASR_EPI_RESID:
-      if (!am && !bm) return launch_single<TASR_EPI_RESID, false, false>(a, p, st);
+      if (!am && !bm) {
+        // FFN down-projection (K = dff): 16-32 k-blocks per tile, so operand look-ahead is worth more than a second
+        // staging buffer (34.0 -> 31.4 us at d = 256, 73.0 -> 68.8 us at d = 512; 256-wide tiles were slower)
+        if (a->K >= 1024 && !use_wide(a->M, a->N, p.splits)) return launch_tc<TASR_EPI_RESID, 128, 6, 1, false, false>(a, p, st);
+        return launch_single<TASR_EPI_RESID, false, false>(a, p, st);
+      }
       break;
     case TASR_EPI_ROPE:
       if (am || bm || a->out_f32 || a->aux == nullptr || a->n_half <= 0 || a->remap_p0 <= 0 || (a->remap_p0 % 64) ||
