@@ -591,13 +591,19 @@ extern "C" int tasr_gemm_bf16(const tasr_gemm_args* a, tasr_stream_t stream) {
       if (!am && !bm) return launch_single<TASR_EPI_SILU, false, false>(a, p, st);
       break;
     case TASR_EPI_SWIGLU_BWD:
-      if (!am && bm) return launch_single<TASR_EPI_SWIGLU_BWD, false, true>(a, p, st);
+      // always 128-wide tiles: with 256-wide ones a super-group walks two column groups per tile and the saved
+      // gate|up tile of the second one is fetched with nothing to hide it (measured: 50.5 vs 84.4 us at d = 256,
+      // 101 vs 145 us at d = 512, where the round-count model of use_wide() used to pick the wide tile)
+      if (!am && bm) {
+        if (a->K >= 512) return launch_tc<TASR_EPI_SWIGLU_BWD, 128, 5, 2, false, true>(a, p, st);
+        return launch_tc<TASR_EPI_SWIGLU_BWD, 128, 4, 2, false, true>(a, p, st);
+      }
       break;
     case TASR_EPI_GLU_BWD:
-      if (!am && bm) return launch_single<TASR_EPI_GLU_BWD, false, true>(a, p, st);
+      if (!am && bm) return launch_tc<TASR_EPI_GLU_BWD, 128, 4, 2, false, true>(a, p, st);  // see SWIGLU_BWD
       break;
     case TASR_EPI_SILU_BWD:
-      if (!am && bm) return launch_single<TASR_EPI_SILU_BWD, false, true>(a, p, st);
+      if (!am && bm) return launch_single<TASR_EPI_SILU_BWD, false, true>(a, p, st);  // wide tiles measured faster here
       break;
     case TASR_EPI_ATOMIC:
       if (am && bm) return launch_single<TASR_EPI_ATOMIC, true, true>(a, p, st);
