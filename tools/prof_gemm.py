@@ -3,6 +3,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from turkish_asr_model_b200 import _lib as L
+from turkish_asr_model_b200.engine import _split_k
 
 dev = torch.device("cuda:0")
 M, d, dff = 21248, int(os.environ.get("PG_D", "256")), int(os.environ.get("PG_DFF", "1024"))
@@ -19,7 +20,7 @@ drop = float(sys.argv[2]) if len(sys.argv) > 2 else 0.1
 def ff1(): L.gemm(M, dff, d, x, d, W1, d, L.EPI_SWIGLU, h, dff, out2=gv, ldo2=2 * dff, bias=b1, n_half=dff, drop_p=drop, seed=1)
 def ff2(): L.gemm(M, d, dff, h, dff, W2, dff, L.EPI_RESID, out, d, bias=b2, aux=res, ldaux=d, alpha=0.5, drop_p=drop, seed=2)
 def ff2_dgrad(): L.gemm(M, dff, d, dy, d, W2, dff, L.EPI_SWIGLU_BWD, dgv, 2 * dff, b_mn=1, aux=gv, ldaux=2 * dff, n_half=dff, drop_p=drop, seed=1)
-def ff1_wgrad(): L.gemm(2 * dff, d, M, dgv, 2 * dff, x, d, L.EPI_ATOMIC, dW1, d, a_mn=1, b_mn=1, split_k=14)
+def ff1_wgrad(): L.gemm(2 * dff, d, M, dgv, 2 * dff, x, d, L.EPI_ATOMIC, dW1, d, a_mn=1, b_mn=1, split_k=_split_k(2 * dff, d, M))
 def ff1_dgrad(): L.gemm(M, d, 2 * dff, dgv, 2 * dff, W1, d, L.EPI_STORE, dxn, d, b_mn=1)
 def plain(): L.gemm(M, 2 * dff, d, x, d, W1, d, L.EPI_STORE, gv, 2 * dff, bias=b1)
 fns = {"ff1": ff1, "ff2": ff2, "ff2_dgrad": ff2_dgrad, "ff1_wgrad": ff1_wgrad, "ff1_dgrad": ff1_dgrad, "plain": plain}
