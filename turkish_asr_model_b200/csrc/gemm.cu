@@ -560,7 +560,9 @@ extern "C" int tasr_gemm_bf16(const tasr_gemm_args* a, tasr_stream_t stream) {
         // block); a single staging buffer pays for a fourth operand stage.  TASR_GEMM_FLAGS=64 restores the narrow tiles.
         if (a->K >= 2048 && !a->out_f32 && a->N % 256 == 0 && !(p.flags & 64))
           return launch_tc<TASR_EPI_STORE, 256, 4, 1, false, true>(a, p, st);
-        if (a->K >= 2048 && !a->out_f32 && !use_wide(a->M, a->N, p.splits))
+        // mid-K data gradients (K = 512 .. 1024): six operand stages and one staging buffer beat four and two by
+        // 4-8 % stand-alone (d = 512: 39.4 -> 36.9 us at K = 1024, 26.7 -> 24.6 us at K = 512); flag 128 = old rule.
+        if (a->K >= ((p.flags & 128) ? 2048 : 512) && !a->out_f32 && !use_wide(a->M, a->N, p.splits))
           return launch_tc<TASR_EPI_STORE, 128, 6, 1, false, true>(a, p, st);
         return launch_single<TASR_EPI_STORE, false, true>(a, p, st);
       }
