@@ -5,6 +5,7 @@
 //   the GLU backward of :82, and the statistics pass of BatchNorm1d :84.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 namespace cg = cooperative_groups;
 
 namespace {
@@ -122,14 +123,34 @@ __global__ void __launch_bounds__(DW_THREADS, 3) dwconv_fwd_kernel(const bf16* _
 }
 
 // Backward, kernel A: du = corr(dw, flipped weight) with the GLU backward fused -> dab (M, 2d) (or du).
+// STAGE: the (a | gate) rows the GLU backward needs are fetched with cp.async into shared memory while the halo tile is
+// staged and the taps run, so the epilogue does not wait on global loads issued after the arithmetic.
+template <bool STAGE>
 __global__ void __launch_bounds__(DW_THREADS, 3) dwconv_bwd_data_kernel(const bf16* __restrict__ dwv, const bf16* __restrict__ ab,
                                                                         int T, int d, const float* __restrict__ weight,
                                                                         bf16* __restrict__ dab, bf16* __restrict__ du_out) {
   __shared__ __align__(16) bf162 tile[ROWS][CC / 2];
   __shared__ __align__(16) float2 wsm[KW][CC / 2];
+  extern __shared__ __align__(16) uint8_t dw_dyn[];
+  bf162 (*abt)[2][CC / 2] = reinterpret_cast<bf162 (*)[2][CC / 2]>(dw_dyn);  // [TT][a | gate][channel pair]
   const int c0 = blockIdx.x * CC, t0 = blockIdx.y * TT, b = blockIdx.z;
   const int lane = threadIdx.x & 31, strip = threadIdx.x >> 5;
   const int ch = c0 + 2 * lane;
+  if (STAGE && ab != nullptr) {
+    // TT rows x 2 halves x 8 chunks of 16 B
+#pragma unroll
+    for (int it = 0; it < TT * 16 / DW_THREADS; ++it) {
+      const int i = threadIdx.x + it * DW_THREADS;
+      const int r = i >> 4, hv = (i >> 3) & 1, v = i & 7;
+      const int t = t0 + r;
+      if (t < T) {
+        const bf16* src = ab + ((long long)b * T + t) * 2 * d + hv * d + c0 + v * 8;
+        const uint32_t dst = smem_u32(&abt[r][hv][v * 4]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   load_weights(wsm, weight, c0);
   load_tile(tile, dwv, b, T, d, t0, c0);
   __syncthreads();
@@ -140,14 +161,24 @@ __global__ void __launch_bounds__(DW_THREADS, 3) dwconv_bwd_data_kernel(const bf
 #pragma unroll
   for (int o = 0; o < OPT; ++o) acc[o] = make_float2(0.f, 0.f);
   conv_strip<true>(tile, lane, strip, wreg, acc);
+  if (STAGE && ab != nullptr) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
 #pragma unroll
   for (int o = 0; o < OPT; ++o) {
-    const int t = t0 + strip * OPT + o;
+    const int tl = strip * OPT + o, t = t0 + tl;
     if (t < T) {
       const long long row = (long long)b * T + t;
       if (ab != nullptr) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + ch));
-        const float2 gt = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + d + ch));
+        float2 a, gt;
+        if (STAGE) {
+          a = __bfloat1622float2(abt[tl][0][lane]);
+          gt = __bfloat1622float2(abt[tl][1][lane]);
+        } else {
+          a = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + ch));
+          gt = __bfloat1622float2(*reinterpret_cast<const bf162*>(ab + row * 2 * d + d + ch));
+        }
         const float s0 = fmaf(0.5f, tanh_approx(0.5f * gt.x), 0.5f), s1 = fmaf(0.5f, tanh_approx(0.5f * gt.y), 0.5f);
         *reinterpret_cast<bf162*>(dab + row * 2 * d + ch) = __floats2bfloat162_rn(acc[o].x * s0, acc[o].y * s1);
         *reinterpret_cast<bf162*>(dab + row * 2 * d + d + ch) =
@@ -295,8 +326,24 @@ extern "C" int tasr_dwconv31_bwd(const void* dw, const void* u, const void* ab, 
   const int ntiles = cdiv(T, TT);
   dim3 grid_a(d / CC, ntiles, B);
   if (dab != nullptr || du != nullptr) {  // data half (main chain)
-    dwconv_bwd_data_kernel<<<grid_a, DW_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dw), reinterpret_cast<const bf16*>(ab), T,
-                                                          d, weight, reinterpret_cast<bf16*>(dab), reinterpret_cast<bf16*>(du));
+    // TASR_DWCONV_STAGE=0: GLU operands read in the epilogue (A/B switch)
+    static const bool stage = [] { const char* e = getenv("TASR_DWCONV_STAGE"); return !(e && e[0] == '0'); }();
+    constexpr int ABSMEM = TT * 2 * (CC / 2) * (int)sizeof(bf162);
+    if (stage && ab != nullptr) {
+      static TasrPerDevice attr_done_a;
+      if (!attr_done_a.get()) {
+        cudaError_t e = cudaFuncSetAttribute(dwconv_bwd_data_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABSMEM);
+        if (e != cudaSuccess) return tasr_set_cuda_error(e);
+        attr_done_a.set();
+      }
+      dwconv_bwd_data_kernel<true><<<grid_a, DW_THREADS, ABSMEM, st>>>(
+          reinterpret_cast<const bf16*>(dw), reinterpret_cast<const bf16*>(ab), T, d, weight, reinterpret_cast<bf16*>(dab),
+          reinterpret_cast<bf16*>(du));
+    } else {
+      dwconv_bwd_data_kernel<false><<<grid_a, DW_THREADS, 0, st>>>(
+          reinterpret_cast<const bf16*>(dw), reinterpret_cast<const bf16*>(ab), T, d, weight, reinterpret_cast<bf16*>(dab),
+          reinterpret_cast<bf16*>(du));
+    }
     TASR_CHECK_LAUNCH();
   }
   if (dweight == nullptr) return TASR_OK;  // weight half is a leaf of the backward graph: callers may run it elsewhere

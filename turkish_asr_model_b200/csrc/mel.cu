@@ -9,6 +9,7 @@
 // and two radix-5 passes in shared memory) + the real-FFT split.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -16,7 +17,7 @@ constexpr int NFFT = 400;
 constexpr int HOP = 160;
 constexpr int NBIN = 201;
 constexpr int FR = 32;         // frames per CTA
-constexpr int MEL_THREADS = 256;
+constexpr int MEL_NT = 512;           // two CTAs (104 KB each) per SM -> 1024 threads per SM
 constexpr int RAW = (FR - 1) * HOP + NFFT;  // 5360 samples staged per CTA
 constexpr int ZLD = 201;       // float2 per frame (200 + 1 pad)
 constexpr int PLD = 203;       // floats per frame of the power spectrum
@@ -78,6 +79,7 @@ __global__ void mel_filter_ranges_kernel(const float* __restrict__ fb, int n_mel
   ranges[n_mels + m] = hi;
 }
 
+template <int MEL_THREADS>
 __global__ void __launch_bounds__(MEL_THREADS)
 mel_logpower_kernel(const float* __restrict__ wave, long long wave_ld, const int* __restrict__ n_samples,
                     const float* __restrict__ window, const float* __restrict__ fb, const int* __restrict__ ranges,
@@ -140,8 +142,10 @@ mel_logpower_kernel(const float* __restrict__ wave, long long wave_ld, const int
     float2 x[8];
 #pragma unroll
     for (int n1 = 0; n1 < 8; ++n1) {
+      // n is even and HOP is even: 8-byte loads, consecutive n2 -> consecutive banks
       const int n = 2 * (25 * n1 + n2);
-      x[n1] = make_float2(r[n] * win[n], r[n + 1] * win[n + 1]);
+      const float2 rv = *reinterpret_cast<const float2*>(r + n), wv = *reinterpret_cast<const float2*>(win + n);
+      x[n1] = make_float2(rv.x * wv.x, rv.y * wv.y);
     }
     dft8(x);
     float2* z = Z + f * ZLD;
@@ -321,13 +325,21 @@ extern "C" int tasr_mel_forward(const float* wave, int64_t wave_ld, const int32_
   const size_t smem = (size_t)RAW * 4 + NFFT * 4 + NFFT * 8 + (size_t)FR * ZLD * 8 + (size_t)FR * PLD * 4 + 2 * 128 * 4 + 200 * 2 + 16;
   static TasrPerDevice attr_done;
   if (!attr_done.get()) {
-    e = cudaFuncSetAttribute(mel_logpower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(mel_logpower_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mel_logpower_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mel_logpower_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tasr_set_cuda_error(e);
     attr_done.set();
   }
   dim3 g1(cdiv(Tmax, FR), B);
-  mel_logpower_kernel<<<g1, MEL_THREADS, smem, st>>>(wave, wave_ld, n_samples, window, fb, ranges, n_mels, feats, Tmax,
-                                                     utt_max);
+  // TASR_MEL_THREADS = 256 (the round-1 CTA size) / 512 / 1024: A/B switch
+  static const int nt = [] { const char* v = getenv("TASR_MEL_THREADS"); return v ? atoi(v) : MEL_NT; }();
+  if (nt == 256)
+    mel_logpower_kernel<256><<<g1, 256, smem, st>>>(wave, wave_ld, n_samples, window, fb, ranges, n_mels, feats, Tmax, utt_max);
+  else if (nt == 1024)
+    mel_logpower_kernel<1024><<<g1, 1024, smem, st>>>(wave, wave_ld, n_samples, window, fb, ranges, n_mels, feats, Tmax, utt_max);
+  else
+    mel_logpower_kernel<512><<<g1, 512, smem, st>>>(wave, wave_ld, n_samples, window, fb, ranges, n_mels, feats, Tmax, utt_max);
   TASR_CHECK_LAUNCH();
   if (normalize) {
     const int fpc = 128;
