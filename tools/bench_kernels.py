@@ -103,3 +103,10 @@ try:
 except Exception as e:  # cos/sin layout differs from the engine's: report and go on
     print("mqa_bwd skipped:", e)
 print("attention fwd flops %.1f GF" % (fl / 1e9))
+
+V, S = 1000, 60
+logits = torch.randn(B, Tp, V, device=dev).bfloat16()
+tg = torch.randint(1, V, (B, S), device=dev)
+il = torch.full((B,), Tp, dtype=torch.int64, device=dev)
+tl = torch.full((B,), S, dtype=torch.int64, device=dev)
+timeit("ctc_loss_fwd_bwd", lambda: L.ctc_loss_fwd_bwd(logits, tg, il, tl), B * Tp * V * 4)

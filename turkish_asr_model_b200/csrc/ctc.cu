@@ -47,13 +47,40 @@ __global__ void __launch_bounds__(256) ctc_rowstats_kernel(const TL* __restrict_
   const int L = (int)min((long long)T, in_len[b]);
   if (t >= L) return;
   const TL* row = logits + ((long long)b * T + t) * ld;
-  float m = NEG_INF;
-  for (int c = lane; c < V; c += 32) m = fmaxf(m, ldlogit(row, c));
-  m = warp_max(m);
-  float s = 0.f;
-  for (int c = lane; c < V; c += 32) s += expf(ldlogit(row, c) - m);
-  s = warp_sum(s);
-  const float lse = m + logf(s);
+  float lse;
+  if (sizeof(TL) == 2 && ((V | (int)ld) & 7) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    // 16-byte loads, one pass: per-lane running maximum and rescaled sum, combined across the warp at the end
+    const uint4* r4 = reinterpret_cast<const uint4*>(row);
+    const int nch = V >> 3;
+    float m = NEG_INF, s = 0.f;
+    for (int c = lane; c < nch; c += 32) {
+      const uint4 q = r4[c];
+      const float2 p0 = unpack_bf16x2(q.x), p1 = unpack_bf16x2(q.y), p2 = unpack_bf16x2(q.z), p3 = unpack_bf16x2(q.w);
+      const float v[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+      float cm = v[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) cm = fmaxf(cm, v[i]);
+      if (cm > m) {
+        s *= expf(m - cm);  // m = -inf on the first chunk: s is 0
+        m = cm;
+      }
+      if (m != NEG_INF) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += expf(v[i] - m);  // a NaN logit makes the row's lse NaN
+      }
+    }
+    const float mw = warp_max(m);
+    s = warp_sum(m == NEG_INF ? 0.f : s * expf(m - mw));
+    lse = mw + logf(s);
+  } else {
+    float m = NEG_INF;
+    for (int c = lane; c < V; c += 32) m = fmaxf(m, ldlogit(row, c));
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < V; c += 32) s += expf(ldlogit(row, c) - m);
+    s = warp_sum(s);
+    lse = m + logf(s);
+  }
   if (lane == 0) lse_out[(long long)b * T + t] = lse;
   const int S = (int)tgt_len[b];
   float* lpr = lp + ((long long)b * T + t) * (Smax + 1);
@@ -124,25 +151,40 @@ __global__ void ctc_alpha_beta_kernel(int T, int Smax, const long long* __restri
     float* nxt = buf1;
     if (dir == 0) cur[2 + s] = active ? v : NEG_INF; else cur[s] = active ? v : NEG_INF;
     __syncthreads();
-    float e_next = NEG_INF;
-    if (active && L > 1) e_next = lpb[(long long)(dir == 0 ? 1 : L - 2) * lp_stride + my_src];
-    for (int step = 1; step < L; ++step) {
-      const int t = dir == 0 ? step : L - 1 - step;
-      const float e = e_next;
-      if (active && step + 1 < L) e_next = lpb[(long long)(dir == 0 ? t + 1 : t - 1) * lp_stride + my_src];
-      float nv = NEG_INF;
-      if (active) {
-        float a0, a1, a2;
-        if (dir == 0) { a0 = cur[2 + s]; a1 = cur[2 + s - 1]; a2 = skip ? cur[2 + s - 2] : NEG_INF; }
-        else { a0 = cur[s]; a1 = cur[s + 1]; a2 = skip ? cur[s + 2] : NEG_INF; }
-        // out-of-lattice neighbours: alpha s-1 < 0 reads the guard (-inf); beta s+1 >= NS reads -inf too
-        if (dir == 1 && s + 1 >= NS) a1 = NEG_INF;
-        nv = lse3(a0, a1, a2) + e;  // NaN logits stay NaN (the loss and the step are then skipped by the trainer)
-        outp[(long long)t * NSmax + s] = nv;
+    // The emission of step t comes from global memory (L2): fetched PF steps ahead into a register ring, otherwise every
+    // step of the serial recursion waits a full L2 round trip (measured: ~800 cycles per step with a one-step prefetch).
+    constexpr int PF = 8;
+    float e_ring[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int st = 1 + u;
+      e_ring[u] = NEG_INF;
+      if (active && st < L) e_ring[u] = lpb[(long long)(dir == 0 ? st : L - 1 - st) * lp_stride + my_src];
+    }
+    for (int base = 1; base < L; base += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int step = base + u;
+        if (step < L) {  // L is uniform over the CTA
+          const int t = dir == 0 ? step : L - 1 - step;
+          const float e = e_ring[u];
+          const int sn = step + PF;
+          if (active && sn < L) e_ring[u] = lpb[(long long)(dir == 0 ? sn : L - 1 - sn) * lp_stride + my_src];
+          float nv = NEG_INF;
+          if (active) {
+            float a0, a1, a2;
+            if (dir == 0) { a0 = cur[2 + s]; a1 = cur[2 + s - 1]; a2 = skip ? cur[2 + s - 2] : NEG_INF; }
+            else { a0 = cur[s]; a1 = cur[s + 1]; a2 = skip ? cur[s + 2] : NEG_INF; }
+            // out-of-lattice neighbours: alpha s-1 < 0 reads the guard (-inf); beta s+1 >= NS reads -inf too
+            if (dir == 1 && s + 1 >= NS) a1 = NEG_INF;
+            nv = lse3(a0, a1, a2) + e;  // NaN logits stay NaN (the loss and the step are then skipped by the trainer)
+            outp[(long long)t * NSmax + s] = nv;
+          }
+          if (dir == 0) nxt[2 + s] = nv; else nxt[s] = nv;
+          __syncthreads();
+          float* tmp = cur; cur = nxt; nxt = tmp;
+        }
       }
-      if (dir == 0) nxt[2 + s] = nv; else nxt[s] = nv;
-      __syncthreads();
-      float* tmp = cur; cur = nxt; nxt = tmp;
     }
     if (dir == 0 && s == 0) {
       const float aL = cur[2 + NS - 1];
@@ -258,11 +300,20 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const TL* __restrict__ lo
   const int S = (int)tgt_len[b];
   const float nll = nll_in[b];
   TG* drow = dlogits + ((long long)b * T + t) * ldg;
+  // bf16 in / bf16 out with 16-byte aligned rows: eight classes per load / store
+  const bool vec = sizeof(TL) == 2 && sizeof(TG) == 2 && ((V | (int)ld | (int)ldg) & 7) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits) |
+                     reinterpret_cast<uintptr_t>(slot_of_class)) & 15) == 0;
   if (t >= L || nll == INFINITY || nll != nll) {
     // padding frames and infeasible samples: exactly 0 (zero_infinity); a NaN sample poisons its rows so that the
     // non-finite gradient norm makes the optimizer skip the step (reference trainer/trainer.py:178-181)
     const float fill = (nll != nll && t < L) ? nll : 0.f;
-    for (int c = lane; c < V; c += 32) store_grad(drow, c, fill);
+    if (vec) {
+      const uint32_t f2 = pack_bf16x2(fill, fill);
+      for (int c = lane; c < (V >> 3); c += 32) reinterpret_cast<uint4*>(drow)[c] = make_uint4(f2, f2, f2, f2);
+    } else {
+      for (int c = lane; c < V; c += 32) store_grad(drow, c, fill);
+    }
     return;
   }
   float* gam = sh_gam + wib * (Smax + 1);
@@ -289,6 +340,26 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const TL* __restrict__ lo
   const float lse = lse_in[(long long)b * T + t];
   const TL* row = logits + ((long long)b * T + t) * ld;
   const unsigned short* slots = slot_of_class + (long long)b * V;
+  if (vec) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(row);
+    const uint4* s4 = reinterpret_cast<const uint4*>(slots);
+    for (int c = lane; c < (V >> 3); c += 32) {
+      const uint4 q = r4[c], sq = s4[c];
+      const uint32_t qw[4] = {q.x, q.y, q.z, q.w}, sw[4] = {sq.x, sq.y, sq.z, sq.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = unpack_bf16x2(qw[i]);
+        float v0 = expf(x.x - lse), v1 = expf(x.y - lse);
+        const uint32_t s0 = sw[i] & 0xFFFFu, s1 = sw[i] >> 16;
+        if (s0 != 0xFFFFu) v0 -= gam[s0];
+        if (s1 != 0xFFFFu) v1 -= gam[s1];
+        ow[i] = pack_bf16x2(v0 * scale, v1 * scale);
+      }
+      reinterpret_cast<uint4*>(drow)[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    return;
+  }
   for (int c = lane; c < V; c += 32) {
     float v = expf(ldlogit(row, c) - lse);
     const unsigned short sl = slots[c];
@@ -331,6 +402,7 @@ extern "C" int tasr_ctc_loss_fwd_bwd(const void* logits, int logits_bf16, int64_
   float* beta = reinterpret_cast<float*>(w); w += (size_t)B * T * (2 * Smax + 1) * 4;
   float* nll_ws = reinterpret_cast<float*>(w); w += (size_t)B * 4;
   int* first_occ = reinterpret_cast<int*>(w); w += (size_t)B * (Smax > 0 ? Smax : 1) * 4;
+  w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w) + 15) & ~(uintptr_t)15);  // 16-byte loads in ctc_grad (slack: +256)
   unsigned short* slots = reinterpret_cast<unsigned short*>(w);
   cudaError_t e = cudaMemsetAsync(slots, 0xFF, (size_t)B * V * 2, st);
   if (e != cudaSuccess) return tasr_set_cuda_error(e);
