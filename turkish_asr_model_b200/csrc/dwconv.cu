@@ -17,13 +17,18 @@ constexpr int OPT = 16;       // outputs per thread
 constexpr int DW_THREADS = 256;  // 32 channel-pair lanes x 8 strips
 constexpr int ROWS = TT + 2 * HALO;
 
-// All global loads of a staging pass are issued before the first shared-memory store (fixed trip counts, values held in
-// registers): a load -> store loop with a run-time bound is compiled into one exposed DRAM round trip per iteration.
-__device__ __forceinline__ void load_tile(bf162 (*tile)[CC / 2], const bf16* __restrict__ src, int b, int T, int d, int t0,
-                                          int c0) {
-  // ROWS x 128 B, 8 threads (16 B each) per row
+// Stages the halo tile (ROWS x 128 B, 8 threads of 16 B per row) and the CTA's weights.  All global loads of both are
+// issued before the first shared-memory store (fixed trip counts, values held in registers): a load -> store loop with a
+// run-time bound is compiled into one exposed DRAM round trip per iteration, and staging the weights and the tile one
+// after the other costs two round trips instead of one.
+// The (d, 31) weight rows of this CTA's 64 channels are one contiguous run: read it coalesced and keep it as
+// [tap][channel pair] so that a thread's 31 taps are conflict-free 8-byte reads.
+__device__ __forceinline__ void load_tile_and_weights(bf162 (*tile)[CC / 2], float2 (*wsm)[CC / 2], const bf16* __restrict__ src,
+                                                      const float* __restrict__ weight, int b, int T, int d, int t0, int c0) {
   constexpr int N = ROWS * 8, IT = (N + DW_THREADS - 1) / DW_THREADS;
+  constexpr int NW = CC * KW, ITW = (NW + DW_THREADS - 1) / DW_THREADS;
   uint4 val[IT];
+  float wv[ITW];
 #pragma unroll
   for (int it = 0; it < IT; ++it) {
     const int i = threadIdx.x + it * DW_THREADS;
@@ -33,28 +38,21 @@ __device__ __forceinline__ void load_tile(bf162 (*tile)[CC / 2], const bf16* __r
     if (i < N && t >= 0 && t < T) val[it] = *reinterpret_cast<const uint4*>(src + ((long long)b * T + t) * d + c0 + v * 8);
   }
 #pragma unroll
+  for (int it = 0; it < ITW; ++it) {
+    const int i = threadIdx.x + it * DW_THREADS;
+    wv[it] = i < NW ? weight[(long long)c0 * KW + i] : 0.f;
+  }
+#pragma unroll
   for (int it = 0; it < IT; ++it) {
     const int i = threadIdx.x + it * DW_THREADS;
     if (i < N) *reinterpret_cast<uint4*>(&tile[i >> 3][(i & 7) * 4]) = val[it];
   }
-}
-
-// The (d, 31) weight rows of this CTA's 64 channels are one contiguous run: read it coalesced and keep it as
-// [tap][channel pair] so that a thread's 31 taps are conflict-free 8-byte reads.
-__device__ __forceinline__ void load_weights(float2 (*wsm)[CC / 2], const float* __restrict__ weight, int c0) {
   float* flat = reinterpret_cast<float*>(wsm);
-  constexpr int N = CC * KW, IT = (N + DW_THREADS - 1) / DW_THREADS;
-  float val[IT];
 #pragma unroll
-  for (int it = 0; it < IT; ++it) {
-    const int i = threadIdx.x + it * DW_THREADS;
-    val[it] = i < N ? weight[(long long)c0 * KW + i] : 0.f;
-  }
-#pragma unroll
-  for (int it = 0; it < IT; ++it) {
+  for (int it = 0; it < ITW; ++it) {
     const int i = threadIdx.x + it * DW_THREADS;
     const int c = i / KW, k = i - c * KW;
-    if (i < N) flat[(k * (CC / 2) + (c >> 1)) * 2 + (c & 1)] = val[it];
+    if (i < NW) flat[(k * (CC / 2) + (c >> 1)) * 2 + (c & 1)] = wv[it];
   }
 }
 
@@ -83,8 +81,7 @@ __global__ void __launch_bounds__(DW_THREADS, 3) dwconv_fwd_kernel(const bf16* _
   __shared__ float red[8][CC][2];
   const int c0 = blockIdx.x * CC, t0 = blockIdx.y * TT, b = blockIdx.z;
   const int lane = threadIdx.x & 31, strip = threadIdx.x >> 5;
-  load_weights(wsm, weight, c0);
-  load_tile(tile, u, b, T, d, t0, c0);
+  load_tile_and_weights(tile, wsm, u, weight, b, T, d, t0, c0);
   const int ch = c0 + 2 * lane;
   const float2 bv = make_float2(bias[ch], bias[ch + 1]);
   __syncthreads();
@@ -151,8 +148,7 @@ __global__ void __launch_bounds__(DW_THREADS, 3) dwconv_bwd_data_kernel(const bf
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  load_weights(wsm, weight, c0);
-  load_tile(tile, dwv, b, T, d, t0, c0);
+  load_tile_and_weights(tile, wsm, dwv, weight, b, T, d, t0, c0);
   __syncthreads();
   float2 wreg[KW];
 #pragma unroll

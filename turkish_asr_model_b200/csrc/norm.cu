@@ -4,6 +4,7 @@
 // Replaces (reference): model/conformer.py:45-49 TransposeGroupNorm.forward (2 transposes +
 //   native_group_norm) and its backward; :84-85 BatchNorm1d + SiLU in ConformerConvModule.
 #include "common.cuh"
+#include <stdlib.h>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -457,6 +458,109 @@ gn_fused_fwd_kernel(const float* __restrict__ x, int T, int d, int G, int rows_p
   }
 }
 
+// Same kernel with the CTA's rows held on chip between the statistics and the normalisation (at most RREG + RSH rows
+// per thread: the first RREG stay in registers, the others in shared memory): all loads of the slice are in flight at
+// once and x is not read a second time, not even from L2.  Same summation order as gn_fused_fwd_kernel, so the results
+// are bit-identical.
+template <bool OUT_BF16, int RREG, int RSH>
+__global__ void __launch_bounds__(NT, 4)
+gn_fused_fwd_reg_kernel(const float* __restrict__ x, int T, int d, int G, int rows_per_cta, float eps,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, void* __restrict__ out,
+                        float* __restrict__ stats_out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float part[64][2];
+  __shared__ float sh_s[NT], sh_ss[NT];
+  __shared__ float sh_mean[64], sh_rstd[64];
+  __shared__ float4 stash[RSH][NT];
+  const int ncl = (int)cluster.num_blocks();
+  const int b = blockIdx.x / ncl, rank = blockIdx.x % ncl;
+  const int tpr = d >> 2, rlanes = NT / tpr;
+  const int col = (threadIdx.x % tpr) << 2, rl = threadIdx.x / tpr;
+  const int t0 = rank * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
+  const long long base = ((long long)b * T + t0 + rl) * d + col;
+  const long long rstride = (long long)rlanes * d;
+  // rows RREG.. go straight to shared memory (cp.async: no registers held while they are in flight)
+#pragma unroll
+  for (int i = 0; i < RSH; ++i)
+    if (t0 + rl + (RREG + i) * rlanes < t1)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&stash[i][threadIdx.x])),
+                   "l"(x + base + (RREG + i) * rstride)
+                   : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  float4 v[RREG];
+#pragma unroll
+  for (int i = 0; i < RREG; ++i) {
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t0 + rl + i * rlanes < t1) v[i] = ld4(x + base + i * rstride);
+  }
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < RREG; ++i) {
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");  // a thread only ever reads the stash entries it fetched itself
+#pragma unroll
+  for (int i = 0; i < RSH; ++i)
+    if (t0 + rl + (RREG + i) * rlanes < t1) {
+      const float4 h = stash[i][threadIdx.x];
+      s += (h.x + h.y) + (h.z + h.w);
+      ss += (h.x * h.x + h.y * h.y) + (h.z * h.z + h.w * h.w);
+    }
+  sh_s[threadIdx.x] = s;
+  sh_ss[threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int tpg = (d / G) >> 2;
+    float a = 0.f, c = 0.f;
+    for (int r = 0; r < rlanes; ++r)
+      for (int j = 0; j < tpg; ++j) {
+        const int idx = r * tpr + threadIdx.x * tpg + j;
+        a += sh_s[idx];
+        c += sh_ss[idx];
+      }
+    part[threadIdx.x][0] = a;
+    part[threadIdx.x][1] = c;
+  }
+  cluster.sync();
+  if (threadIdx.x < G) {
+    double a = 0.0, c = 0.0;
+    for (int r = 0; r < ncl; ++r) {
+      const float* rp = cluster.map_shared_rank(&part[0][0], r);
+      a += rp[threadIdx.x * 2];
+      c += rp[threadIdx.x * 2 + 1];
+    }
+    const double n = (double)T * (d / G);
+    const double mean = a / n;
+    double var = c / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    sh_mean[threadIdx.x] = (float)mean;
+    sh_rstd[threadIdx.x] = rstd;
+    if (rank == 0 && stats_out != nullptr) {
+      stats_out[((long long)b * G + threadIdx.x) * 2] = (float)mean;
+      stats_out[((long long)b * G + threadIdx.x) * 2 + 1] = rstd;
+    }
+  }
+  cluster.sync();  // also keeps every CTA's `part` alive until all peers have read it
+  const int g = col / (d / G);
+  const float mean = sh_mean[g], rstd = sh_rstd[g];
+  const float4 ga = ld4(gamma + col), be = ld4(beta + col);
+#pragma unroll
+  for (int i = 0; i < RREG + RSH; ++i) {
+    if (t0 + rl + i * rlanes < t1) {
+      const long long off = base + i * rstride;
+      float4 w = i < RREG ? v[i < RREG ? i : 0] : stash[i < RREG ? 0 : i - RREG][threadIdx.x];  // own values: no barrier needed
+      w.x = (w.x - mean) * rstd * ga.x + be.x;
+      w.y = (w.y - mean) * rstd * ga.y + be.y;
+      w.z = (w.z - mean) * rstd * ga.z + be.z;
+      w.w = (w.w - mean) * rstd * ga.w + be.w;
+      if (OUT_BF16) st4_bf16(reinterpret_cast<bf16*>(out) + off, w);
+      else *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + off) = w;
+    }
+  }
+}
+
 // backward: dx = rstd * (dy*gamma - S1/n - xhat*S2/n); per-channel sums of dy*xhat and dy exchanged through DSMEM
 template <bool DY_BF16>
 __global__ void __launch_bounds__(NT, 4)
@@ -620,6 +724,18 @@ extern "C" int tasr_groupnorm_fwd(const float* x, int B, int T, int d, int G, fl
   if ((long long)T * d * sizeof(float) <= GN_FUSED_MAX_SLICE) {  // one cluster per utterance; its slice is re-read through L2
     const int cl = gn_cluster_size(B, T, 6);
     const int frows = cdiv(T, cl);
+    // rows of a CTA's slice per thread; up to GN_REG_ROWS of them stay on chip (TASR_GN_REG=0: always re-read from L2)
+    constexpr int GN_RREG = 4, GN_RSH = 8, GN_REG_ROWS = GN_RREG + GN_RSH;
+    static const bool reg_ok = [] { const char* v = getenv("TASR_GN_REG"); return !(v && v[0] == '0'); }();
+    if (reg_ok && d <= 4 * NT && NT % (d / 4) == 0 && cdiv(frows, NT / (d / 4)) <= GN_REG_ROWS) {
+      cudaError_t e = out_bf16 ? gn_launch_cluster(gn_fused_fwd_reg_kernel<true, GN_RREG, GN_RSH>, B, cl, 0, st, x, T, d, G, frows, eps,
+                                                   gamma, beta, out, stats)
+                               : gn_launch_cluster(gn_fused_fwd_reg_kernel<false, GN_RREG, GN_RSH>, B, cl, 0, st, x, T, d, G, frows, eps,
+                                                   gamma, beta, out, stats);
+      if (e != cudaSuccess) return tasr_set_cuda_error(e);
+      TASR_CHECK_LAUNCH();
+      return TASR_OK;
+    }
     cudaError_t e = out_bf16 ? gn_launch_cluster(gn_fused_fwd_kernel<true>, B, cl, 0, st, x, T, d, G, frows, eps, gamma, beta, out, stats)
                              : gn_launch_cluster(gn_fused_fwd_kernel<false>, B, cl, 0, st, x, T, d, G, frows, eps, gamma, beta, out, stats);
     if (e != cudaSuccess) return tasr_set_cuda_error(e);
