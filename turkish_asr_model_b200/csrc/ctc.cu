@@ -154,39 +154,53 @@ __global__ void ctc_alpha_beta_kernel(int T, int Smax, const long long* __restri
     __syncthreads();
     // The emission of step t comes from global memory (L2): fetched PF steps ahead into a register ring, otherwise every
     // step of the serial recursion waits a full L2 round trip (measured: ~800 cycles per step with a one-step prefetch).
+    // The loads are unconditional (clamped row, column 0 for idle threads; the surplus values are never consumed): a
+    // predicated load is compiled into load + select, and the select waits for the load inside the same step.
     constexpr int PF = 8;
     float e_ring[PF];
+    const float* lpe = lpb + (active ? my_src : 0);
 #pragma unroll
     for (int u = 0; u < PF; ++u) {
-      const int st = 1 + u;
-      e_ring[u] = NEG_INF;
-      if (active && st < L) e_ring[u] = lpb[(long long)(dir == 0 ? st : L - 1 - st) * lp_stride + my_src];
+      const int st = min(1 + u, L - 1);
+      e_ring[u] = lpe[(long long)(dir == 0 ? st : L - 1 - st) * lp_stride];
     }
-    for (int base = 1; base < L; base += PF) {
+    auto lattice_step = [&](int step, float e) {
+      const int t = dir == 0 ? step : L - 1 - step;
+      float nv = NEG_INF;
+      if (active) {
+        float a0, a1, a2;
+        if (dir == 0) { a0 = cur[2 + s]; a1 = cur[2 + s - 1]; a2 = skip ? cur[2 + s - 2] : NEG_INF; }
+        else { a0 = cur[s]; a1 = cur[s + 1]; a2 = skip ? cur[s + 2] : NEG_INF; }
+        // out-of-lattice neighbours: alpha s-1 < 0 reads the guard (-inf); beta s+1 >= NS reads -inf too
+        if (dir == 1 && s + 1 >= NS) a1 = NEG_INF;
+        // NaN logits stay NaN (the loss and the step are then skipped by the trainer).  ex2.approx / lg2.approx in place
+        // of expf / logf were measured: no change (118.3 -> 117.4 us), the step is not bound by this arithmetic.
+        nv = lse3(a0, a1, a2) + e;
+        outp[(long long)t * NSmax + s] = nv;
+      }
+      if (dir == 0) nxt[2 + s] = nv; else nxt[s] = nv;
+    };
+    // full groups of PF steps: no guard inside, and a ring slot is refilled only after its value has been consumed, so
+    // the load lands in the slot's own register (a guard or an early refill costs a register move that waits for the load)
+    int base = 1;
+    for (; base + PF <= L; base += PF) {
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         const int step = base + u;
-        if (step < L) {  // L is uniform over the CTA
-          const int t = dir == 0 ? step : L - 1 - step;
-          const float e = e_ring[u];
-          const int sn = step + PF;
-          if (active && sn < L) e_ring[u] = lpb[(long long)(dir == 0 ? sn : L - 1 - sn) * lp_stride + my_src];
-          float nv = NEG_INF;
-          if (active) {
-            float a0, a1, a2;
-            if (dir == 0) { a0 = cur[2 + s]; a1 = cur[2 + s - 1]; a2 = skip ? cur[2 + s - 2] : NEG_INF; }
-            else { a0 = cur[s]; a1 = cur[s + 1]; a2 = skip ? cur[s + 2] : NEG_INF; }
-            // out-of-lattice neighbours: alpha s-1 < 0 reads the guard (-inf); beta s+1 >= NS reads -inf too
-            if (dir == 1 && s + 1 >= NS) a1 = NEG_INF;
-            // NaN logits stay NaN (the loss and the step are then skipped by the trainer).  ex2.approx / lg2.approx in place
-            // of expf / logf were measured: no change (118.3 -> 117.4 us), the step is not bound by this arithmetic.
-            nv = lse3(a0, a1, a2) + e;
-            outp[(long long)t * NSmax + s] = nv;
-          }
-          if (dir == 0) nxt[2 + s] = nv; else nxt[s] = nv;
-          __syncthreads();
-          float* tmp = cur; cur = nxt; nxt = tmp;
-        }
+        lattice_step(step, e_ring[u]);
+        const int sn = min(step + PF, L - 1);
+        e_ring[u] = lpe[(long long)(dir == 0 ? sn : L - 1 - sn) * lp_stride];
+        __syncthreads();
+        float* tmp = cur; cur = nxt; nxt = tmp;
+      }
+    }
+    // the last L - base < PF steps: their emissions are already in the ring
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      if (base + u < L) {  // L is uniform over the CTA
+        lattice_step(base + u, e_ring[u]);
+        __syncthreads();
+        float* tmp = cur; cur = nxt; nxt = tmp;
       }
     }
     if (dir == 0 && s == 0) {
